@@ -160,13 +160,23 @@ void orc_slos_layer_scatter(int m, int k, const double *u, int mk, const double 
 
 /* Same layer in gather form (mathematically identical; used as the threaded CPU baseline):
  *   c_k[s] = sum_{j: s_j>0} U[j,mk] * c_{k-1}[s - e_j]            
- * computes children [begin,end). */
+ * computes children [begin,end).  Ranks use the collapsed (hockey-stick) form of SURVEY.md 8a row a1,
+ *   rank(s) = sum_{i<m-1} C(T_i-1+q_i, q_i),  T_i = photons right of mode i, q_i = m-1-i,
+ * through a per-call binomial table, so that the baseline is a fair multithreaded CPU implementation and not a
+ * strawman; it is checked against the literal scatter loop above in tests/test_oracle_golden.py. */
 void orc_slos_layer_gather(int m, int k, const double *u, int mk, const double *parent, double *child,
                            uint64_t begin, uint64_t end)
 {
     const cplx *U = (const cplx *)u;
     const cplx *P = (const cplx *)parent;
     cplx *C = (cplx *)child;
+    /* bt[q][T] = C(T-1+q, q) for T >= 1, 0 for T = 0 */
+    int W = k + 1;
+    uint64_t *bt = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m * (size_t)W);
+    for (int q = 0; q < m; ++q)
+        for (int T = 0; T <= k; ++T) bt[q * W + T] = T ? orc_binom(T - 1 + q, q) : 0;
+    cplx ucol[ORC_MAXM];
+    for (int j = 0; j < m; ++j) ucol[j] = U[(size_t)j * m + mk];
 #pragma omp parallel
     {
         int nt = 1, tid = 0;
@@ -182,17 +192,21 @@ void orc_slos_layer_gather(int m, int k, const double *u, int mk, const double *
             orc_unrank(m, k, lo, s);
             for (uint64_t r = lo; r < hi; ++r) {
                 cplx acc = 0;
+                /* parent rank for mode j = r - sum_{i<j} (bt[q_i][T_i] - bt[q_i][T_i-1]) */
+                uint64_t E = 0;
+                int T = k;
                 for (int j = 0; j < m; ++j) {
-                    if (!s[j]) continue;
-                    s[j] -= 1;
-                    acc += U[(size_t)j * m + mk] * P[orc_rank(m, k - 1, s)];
-                    s[j] += 1;
+                    if (s[j]) acc += ucol[j] * P[r - E];
+                    T -= s[j];
+                    if (T == 0) break;
+                    if (j < m - 1) E += bt[(m - 1 - j) * W + T] - bt[(m - 1 - j) * W + T - 1];
                 }
                 C[r - begin] = acc;
                 orc_next(m, s);
             }
         }
     }
+    free(bt);
 }
 
 /* Photon insertion order of a single input state: reference _slos.py:61-86 (_Path._decompose with one

@@ -1,0 +1,108 @@
+// common.cuh -- shared helpers for libfock_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fock_b200.h"
+
+#define FOCK_QMAX 64   // max modes for rank / SLOS kernels
+#define FOCK_TMAX 33   // photons 0..32
+#define FOCK_NMAX 32
+
+struct fock_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t total_mem;
+    uint64_t *d_bt;   // [FOCK_QMAX][FOCK_TMAX]  Bt[q][T] = C(T-1+q, q), 0 for T==0, saturating
+    uint64_t *d_dt;   // [FOCK_QMAX][FOCK_TMAX]  Dt[q][T] = Bt[q][T]-Bt[q][T-1]
+    int *d_status;    // device-side error flag
+    double *d_scratch; // small scratch (sum accumulators)
+    uint64_t launches;
+};
+
+void fock_set_error(const char *fmt, ...);
+int fock_check_cuda(cudaError_t e, const char *what);
+const uint64_t *fock_host_bt();  // host copy of Bt
+const uint64_t *fock_host_dt();
+
+#define FOCK_CUDA(x)                                              \
+    do {                                                          \
+        int _rc = fock_check_cuda((x), #x);                       \
+        if (_rc) return _rc;                                      \
+    } while (0)
+
+#define FOCK_REQUIRE(cond, code, ...)                             \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            fock_set_error(__VA_ARGS__);                          \
+            return (code);                                        \
+        }                                                         \
+    } while (0)
+
+struct ScopedDevice {
+    int prev;
+    explicit ScopedDevice(int dev) : prev(-1) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~ScopedDevice() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---------------------------------------------------------------- complex helpers (double2 = re, im)
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
+    double re = fma(a.x, b.x, c.x);
+    double im = fma(a.x, b.y, c.y);
+    re = fma(-a.y, b.y, re);
+    im = fma(a.y, b.x, im);
+    return make_double2(re, im);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// streaming 16-byte accesses
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double2 *p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (same keying as oracle/fock_oracle.c)
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_hi, uint64_t ctr_lo, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// d-th uniform double in [0,1) of sample idx
+__host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t idx, uint32_t d) {
+    uint32_t w[4];
+    philox4x32_10(seed, idx, (uint64_t)(d >> 1), w);
+    uint32_t a = w[(d & 1) * 2], b = w[(d & 1) * 2 + 1];
+    uint64_t bits = (((uint64_t)a << 32) | b) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

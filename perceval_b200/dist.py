@@ -1,0 +1,176 @@
+"""Multi-GPU partitioning of the Fock-amplitude path: one process per GPU, torch.distributed (NCCL over NVLink) plumbing.
+
+* SLOS -- owner-computes on the child layer.  Every rank owns a contiguous rank range of each child layer; the parent
+  layer must be resident where it is read, so after each intermediate layer the shards are exchanged with ONE
+  all-gather (``exchange="allgather"``, the scheme BASELINE.json's north_star names).  Because NVLink (~0.7 TB/s
+  all-gather bus bandwidth) is slower than re-computing a layer from HBM, ``exchange="replicate"`` instead lets every
+  rank recompute the (small) intermediate layers redundantly with no communication at all; ``"auto"`` picks per layer
+  from a bandwidth model.  The last layer (two thirds of all traffic) is always sharded and stays sharded; only the
+  scalar sum(p) is all-reduced.  Results are independent of the world size bit for bit (each child is computed by the
+  same kernel from the same parent values).
+* permanents -- a batch is split by matrix; a single large permanent is split by Gray-code range with one all-reduce.
+* sampling -- the Philox stream is keyed by the global sample index, so ranks draw disjoint index ranges and an optional
+  all-gather restores the chronological order.
+
+The compute step is injected (``layer_fn`` ...) so that the partition / exchange logic is testable on CPU with gloo.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced split of [0, total): the first (total % world) ranks get one extra element."""
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_gather_ragged(shard: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """All-gather of balanced contiguous shards (see shard_range) of a 1-D tensor of length ``total``."""
+    rank, world = _world(group)
+    if world == 1:
+        return shard
+    is_complex = shard.is_complex()
+    flat = torch.view_as_real(shard).reshape(-1) if is_complex else shard.reshape(-1)
+    width = 2 if is_complex else 1
+    maxlen = (total + world - 1) // world * width
+    send = flat
+    if flat.numel() < maxlen:
+        send = torch.zeros(maxlen, dtype=flat.dtype, device=flat.device)
+        send[:flat.numel()] = flat
+    recv = torch.empty(world * maxlen, dtype=flat.dtype, device=flat.device)
+    try:
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):
+        chunks = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(chunks, send.contiguous(), group=group)
+        recv = torch.cat(chunks)
+    if total % world == 0:
+        out = recv
+    else:
+        parts = []
+        for r in range(world):
+            b, e = shard_range(total, r, world)
+            parts.append(recv[r * maxlen: r * maxlen + (e - b) * width])
+        out = torch.cat(parts)
+    return torch.view_as_complex(out.view(-1, 2)) if is_complex else out
+
+
+# measured-ish bandwidth model (GB/s) used by exchange="auto"; see DESIGN.md section 6
+HBM_EFFECTIVE_GBS = 2500.0
+NVLINK_ALLGATHER_GBS = 700.0
+
+
+def choose_exchange(n_parent: int, n_child: int, world: int) -> str:
+    """'replicate' if recomputing the whole child layer on every rank is cheaper than all-gathering its shards."""
+    if world == 1:
+        return "replicate"
+    extra_compute = 16.0 * (n_parent + n_child) * (1.0 - 1.0 / world) / HBM_EFFECTIVE_GBS
+    gather = 16.0 * n_child * (world - 1) / world / NVLINK_ALLGATHER_GBS
+    return "replicate" if extra_compute <= gather else "allgather"
+
+
+def slos_probs_sharded(m: int, in_state, order, count_fn, layer_fn, last_fn, group=None, exchange: str = "auto"):
+    """Layer-sharded SLOS chain.
+
+    count_fn(m, k) -> N(k);  layer_fn(k, mk, parent_full, begin, end) -> child[begin:end] (complex128 1-D tensor);
+    last_fn(k, mk, parent_full, begin, end) -> (probs[begin:end], partial_sum tensor of 1 element).
+    Returns (probs_shard, (begin, end), total_sum tensor, exchanges) where exchanges lists the decision per layer."""
+    rank, world = _world(group)
+    n = sum(int(x) for x in in_state)
+    decisions = []
+    parent = None  # layer 0 is created by the first layer_fn call (parent_full=None means the vacuum coefficient [1])
+    for k in range(1, n):
+        nc, npar = count_fn(m, k), count_fn(m, k - 1)
+        mode = exchange if exchange != "auto" else choose_exchange(npar, nc, world)
+        if world == 1:
+            mode = "replicate"
+        decisions.append(mode)
+        if mode == "replicate":
+            parent = layer_fn(k, order[k - 1], parent, 0, nc)
+        else:
+            b, e = shard_range(nc, rank, world)
+            shard = layer_fn(k, order[k - 1], parent, b, e)
+            parent = all_gather_ragged(shard, nc, group)
+    N = count_fn(m, n)
+    b, e = shard_range(N, rank, world)
+    probs, psum = last_fn(n, order[n - 1], parent, b, e)
+    if world > 1:
+        dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)
+    return probs, (b, e), psum, decisions
+
+
+def engine_slos_probs_sharded(engine, U, in_state, group=None, exchange: str = "auto"):
+    """The device instantiation of slos_probs_sharded (kernels from libfock_b200.so, NCCL all-gather)."""
+    from .engine import prodnfact
+    occ = [int(x) for x in in_state]
+    m, n = len(occ), sum(occ)
+    assert n >= 1
+    order = engine.slos_order(occ)
+    inf = prodnfact(occ)
+
+    def vac():
+        return torch.ones(1, dtype=torch.complex128, device=engine.device)
+
+    def layer_fn(k, mk, parent, b, e):
+        parent = vac() if parent is None else parent
+        return engine.slos_layer(m, k, U, mk, parent, child_begin=b, child_end=e)
+
+    def last_fn(k, mk, parent, b, e):
+        parent = vac() if parent is None else parent
+        psum = torch.zeros(1, dtype=torch.float64, device=engine.device)
+        probs = engine.slos_layer_probs(m, k, U, mk, parent, inf, psum=psum, child_begin=b, child_end=e)
+        return probs, psum
+
+    return slos_probs_sharded(m, occ, order, engine.count, layer_fn, last_fn, group, exchange)
+
+
+def permanents_sharded(perm_fn, mats: torch.Tensor, group=None):
+    """Batch of permanents over ranks.  perm_fn(mats, gray_begin, gray_end) -> (B,) complex tensor (partial sums for a
+    Gray sub-range, already scaled).  B >= world: split by matrix + all-gather; else split the Gray range + all-reduce."""
+    rank, world = _world(group)
+    B, n = mats.shape[0], mats.shape[1]
+    if world == 1:
+        return perm_fn(mats, 0, 0)
+    if B >= world:
+        b, e = shard_range(B, rank, world)
+        part = perm_fn(mats[b:e], 0, 0)
+        return all_gather_ragged(part, B, group)
+    G = 1 << max(n - 1, 0)
+    b, e = shard_range(G, rank, world)
+    part = perm_fn(mats, b, e) if e > b else torch.zeros(B, dtype=torch.complex128, device=mats.device)
+    buf = torch.view_as_real(part).contiguous()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return torch.view_as_complex(buf)
+
+
+def samples_sharded(sample_fn, count: int, offset: int = 0, group=None, gather: bool = True):
+    """sample_fn(count, offset) -> (count, m) uint8 tensor of the samples with global indices [offset, offset+count)."""
+    rank, world = _world(group)
+    b, e = shard_range(count, rank, world)
+    part = sample_fn(e - b, offset + b)
+    if world == 1 or not gather:
+        return part
+    m = part.shape[1]
+    flat = all_gather_ragged(part.reshape(-1), count * m, group) if (count % world == 0) else None
+    if flat is None:
+        # ragged in units of whole samples: gather per-sample padded
+        maxc = (count + world - 1) // world
+        send = torch.zeros((maxc, m), dtype=part.dtype, device=part.device)
+        send[: e - b] = part
+        chunks = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(chunks, send, group=group)
+        outs = []
+        for r in range(world):
+            rb, re_ = shard_range(count, r, world)
+            outs.append(chunks[r][: re_ - rb])
+        return torch.cat(outs)
+    return flat.view(count, m)

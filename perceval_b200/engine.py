@@ -1,0 +1,255 @@
+"""Torch-facing wrapper of the C ABI: owns device tensors, passes raw pointers + the current CUDA stream.
+
+PyTorch is plumbing only (device memory, streams, DLPack); every number is produced by the hand-written sm_100a
+kernels in libfock_b200.so.  All entry points raise if CUDA / the library is unavailable -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FockError, check
+
+
+def _state_u8(state) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(list(state), dtype=np.uint8))
+
+
+def prodnfact(state) -> float:
+    p = 1.0
+    for x in state:
+        for v in range(2, int(x) + 1):
+            p *= v
+    return p
+
+
+class FockEngine:
+    """One engine per CUDA device."""
+
+    _engines: dict = {}
+
+    @classmethod
+    def get(cls, device=None) -> "FockEngine":
+        idx = cls._device_index(device)
+        eng = cls._engines.get(idx)
+        if eng is None:
+            eng = cls(idx)
+            cls._engines[idx] = eng
+        return eng
+
+    @staticmethod
+    def _device_index(device) -> int:
+        if not torch.cuda.is_available():
+            raise FockError("perceval_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            return torch.cuda.current_device()
+        if isinstance(device, int):
+            return device
+        d = torch.device(device)
+        return d.index if d.index is not None else torch.cuda.current_device()
+
+    def __init__(self, index: int):
+        self.index = index
+        self.device = torch.device("cuda", index)
+        self.lib = _lib.load()
+        self.ctx = _lib.context(index)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.fock_launch_count(self.ctx))
+
+    def check_status(self):
+        check(self.lib.fock_check_status(self.ctx, self._stream()), "fock_check_status")
+
+    def unitary(self, u) -> torch.Tensor:
+        """m x m complex128 device tensor from numpy / torch / anything exposing __dlpack__ or __array__."""
+        if isinstance(u, torch.Tensor):
+            t = u
+        elif hasattr(u, "__dlpack__") and not isinstance(u, np.ndarray):
+            t = torch.from_dlpack(u)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(u, dtype=np.complex128)))
+        t = t.to(device=self.device, dtype=torch.complex128).contiguous()
+        if t.dim() != 2 or t.shape[0] != t.shape[1]:
+            raise ValueError("unitary must be a square matrix")
+        return t
+
+    # ------------------------------------------------------------------ FSArray
+    def count(self, m: int, n: int) -> int:
+        return _lib.count(m, n)
+
+    def rank(self, m: int, n: int, states: torch.Tensor) -> torch.Tensor:
+        states = states.to(device=self.device, dtype=torch.uint8).contiguous().view(-1, m)
+        out = torch.empty(states.shape[0], dtype=torch.int64, device=self.device)
+        check(self.lib.fock_rank(self.ctx, m, n, states.data_ptr(), states.shape[0], out.data_ptr(), self._stream()), "fock_rank")
+        return out
+
+    def unrank(self, m: int, n: int, ranks: torch.Tensor) -> torch.Tensor:
+        ranks = ranks.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
+        out = torch.empty((ranks.shape[0], m), dtype=torch.uint8, device=self.device)
+        check(self.lib.fock_unrank(self.ctx, m, n, ranks.data_ptr(), ranks.shape[0], out.data_ptr(), self._stream()), "fock_unrank")
+        return out
+
+    def enumerate(self, m: int, n: int, begin: int = 0, end: int | None = None) -> torch.Tensor:
+        end = self.count(m, n) if end is None else end
+        out = torch.empty((end - begin, m), dtype=torch.uint8, device=self.device)
+        check(self.lib.fock_enumerate(self.ctx, m, n, begin, end, out.data_ptr(), self._stream()), "fock_enumerate")
+        return out
+
+    # ------------------------------------------------------------------ SLOS
+    def slos_order(self, state) -> list:
+        s = _state_u8(state)
+        n = int(s.sum())
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        check(self.lib.slos_order(len(s), s.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)), "slos_order")
+        return [int(x) for x in out[:n]]
+
+    def slos_layer(self, m: int, k: int, U: torch.Tensor, mk: int, parent: torch.Tensor, child: torch.Tensor | None = None,
+                   parent_begin: int = 0, child_begin: int = 0, child_end: int | None = None) -> torch.Tensor:
+        """One layer (C ABI slos_layer).  parent holds ranks [parent_begin, parent_begin+len)."""
+        child_end = self.count(m, k) if child_end is None else child_end
+        if child is None:
+            child = torch.empty(child_end - child_begin, dtype=torch.complex128, device=self.device)
+        assert child.numel() >= child_end - child_begin
+        check(self.lib.slos_layer(self.ctx, m, k, U.data_ptr(), mk, parent.data_ptr(), parent_begin,
+                                  parent_begin + parent.numel(), child.data_ptr(), child_begin, child_end, self._stream()),
+              "slos_layer")
+        return child
+
+    def slos_layer_probs(self, m: int, k: int, U: torch.Tensor, mk: int, parent: torch.Tensor, in_prodnfact: float,
+                         probs: torch.Tensor | None = None, coefs: torch.Tensor | None = None, psum: torch.Tensor | None = None,
+                         parent_begin: int = 0, child_begin: int = 0, child_end: int | None = None) -> torch.Tensor:
+        child_end = self.count(m, k) if child_end is None else child_end
+        if probs is None:
+            probs = torch.empty(child_end - child_begin, dtype=torch.float64, device=self.device)
+        check(self.lib.slos_layer_probs(self.ctx, m, k, U.data_ptr(), mk, parent.data_ptr(), parent_begin,
+                                        parent_begin + parent.numel(), coefs.data_ptr() if coefs is not None else None,
+                                        probs.data_ptr(), psum.data_ptr() if psum is not None else None, float(in_prodnfact),
+                                        child_begin, child_end, self._stream()), "slos_layer_probs")
+        return probs
+
+    def slos_coefs(self, U: torch.Tensor, in_state) -> torch.Tensor:
+        """Un-normalised SLOS coefficients of the last layer (what _Path.coefs holds, _slos.py:44)."""
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        order = self.slos_order(s)
+        cur = torch.ones(1, dtype=torch.complex128, device=self.device)
+        for k in range(1, n + 1):
+            cur = self.slos_layer(m, k, U, order[k - 1], cur)
+        return cur
+
+    def slos_probs(self, U: torch.Tensor, in_state, want_coefs: bool = False, workspaces=None):
+        """Full output distribution in FSArray order.  Returns (probs, sum, coefs|None).
+
+        Runs the whole chain through the C ABI ``slos_prob_distribution`` with ping-pong workspaces sized for
+        layers n-1 and n-2 (only two layers are ever live)."""
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        N = self.count(m, n)
+        if workspaces is None:
+            wa = torch.empty(self.count(m, n - 1) if n >= 1 else 1, dtype=torch.complex128, device=self.device)
+            wb = torch.empty(self.count(m, n - 2) if n >= 2 else 1, dtype=torch.complex128, device=self.device)
+        else:
+            wa, wb = workspaces
+        probs = torch.empty(N, dtype=torch.float64, device=self.device)
+        psum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        coefs = torch.empty(N, dtype=torch.complex128, device=self.device) if want_coefs else None
+        check(self.lib.slos_prob_distribution(self.ctx, m, U.data_ptr(), s.ctypes.data_as(C.c_void_p), wa.data_ptr(), wb.data_ptr(),
+                                              coefs.data_ptr() if coefs is not None else None, probs.data_ptr(), psum.data_ptr(),
+                                              self._stream()), "slos_prob_distribution")
+        return probs, psum, coefs
+
+    def slos_probs_from_coefs(self, m: int, n: int, coefs: torch.Tensor, in_prodnfact: float):
+        probs = torch.empty(coefs.numel(), dtype=torch.float64, device=self.device)
+        psum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        check(self.lib.slos_probs_epilogue(self.ctx, m, n, coefs.data_ptr(), float(in_prodnfact), probs.data_ptr(), psum.data_ptr(),
+                                           0, coefs.numel(), self._stream()), "slos_probs_epilogue")
+        return probs, psum
+
+    def slos_amplitudes_from_coefs(self, m: int, n: int, coefs: torch.Tensor, in_prodnfact: float) -> torch.Tensor:
+        amps = torch.empty(coefs.numel(), dtype=torch.complex128, device=self.device)
+        check(self.lib.slos_amplitudes_epilogue(self.ctx, m, n, coefs.data_ptr(), float(in_prodnfact), amps.data_ptr(), 0,
+                                                coefs.numel(), self._stream()), "slos_amplitudes_epilogue")
+        return amps
+
+    def slos_probs_host(self, u: np.ndarray, in_state) -> tuple[np.ndarray, float]:
+        """End-to-end call with HOST buffers through the C ABI (U in, probabilities out)."""
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.complex128))
+        probs = np.empty(self.count(m, n), dtype=np.float64)
+        psum = np.zeros(1, dtype=np.float64)
+        check(self.lib.slos_prob_distribution_host(self.ctx, m, u.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                                                   probs.ctypes.data_as(C.c_void_p), psum.ctypes.data_as(C.c_void_p)),
+              "slos_prob_distribution_host")
+        return probs, float(psum[0])
+
+    # ------------------------------------------------------------------ permanents / Naive
+    def permanents(self, mats: torch.Tensor, gray_begin: int = 0, gray_end: int = 0) -> torch.Tensor:
+        """Batched permanents of (B, n, n) complex128 matrices (Glynn); optional Gray-code sub-range."""
+        mats = mats.to(device=self.device, dtype=torch.complex128).contiguous()
+        if mats.dim() == 2:
+            mats = mats.unsqueeze(0)
+        B, n = mats.shape[0], mats.shape[1]
+        assert mats.shape[2] == n
+        out = torch.empty(B, dtype=torch.complex128, device=self.device)
+        check(self.lib.glynn_permanent_batch(self.ctx, n, mats.data_ptr(), B, out.data_ptr(), gray_begin, gray_end, self._stream()),
+              "glynn_permanent_batch")
+        return out
+
+    def permanents_host(self, mats: np.ndarray) -> np.ndarray:
+        mats = np.ascontiguousarray(np.asarray(mats, dtype=np.complex128))
+        if mats.ndim == 2:
+            mats = mats[None]
+        out = np.empty(mats.shape[0], dtype=np.complex128)
+        check(self.lib.glynn_permanent_batch_host(self.ctx, mats.shape[1], mats.ctypes.data_as(C.c_void_p), mats.shape[0],
+                                                  out.ctypes.data_as(C.c_void_p)), "glynn_permanent_batch_host")
+        return out
+
+    def naive_amplitudes(self, U: torch.Tensor, in_state, out_ranks: torch.Tensor | None = None,
+                         out_states: torch.Tensor | None = None) -> torch.Tensor:
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        if out_states is not None:
+            st = out_states.to(device=self.device, dtype=torch.uint8).contiguous().view(-1, m)
+            amps = torch.empty(st.shape[0], dtype=torch.complex128, device=self.device)
+            check(self.lib.naive_amplitudes_states(self.ctx, m, n, U.data_ptr(), s.ctypes.data_as(C.c_void_p), st.data_ptr(),
+                                                   st.shape[0], amps.data_ptr(), self._stream()), "naive_amplitudes_states")
+            return amps
+        rk = out_ranks.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
+        amps = torch.empty(rk.shape[0], dtype=torch.complex128, device=self.device)
+        check(self.lib.naive_amplitudes(self.ctx, m, n, U.data_ptr(), s.ctypes.data_as(C.c_void_p), rk.data_ptr(), rk.shape[0],
+                                        amps.data_ptr(), self._stream()), "naive_amplitudes")
+        return amps
+
+    # ------------------------------------------------------------------ Clifford & Clifford
+    def cc2017_samples(self, U: torch.Tensor, in_state, count: int, seed: int = 0, offset: int = 0,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        if out is None:
+            out = torch.empty((count, m), dtype=torch.uint8, device=self.device)
+        check(self.lib.cc2017_samples(self.ctx, m, n, U.data_ptr(), s.ctypes.data_as(C.c_void_p), count, seed & ((1 << 64) - 1),
+                                      offset, out.data_ptr(), self._stream()), "cc2017_samples")
+        return out
+
+    def cc2017_samples_host(self, u: np.ndarray, in_state, count: int, seed: int = 0, offset: int = 0) -> np.ndarray:
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.complex128))
+        out = np.empty((count, m), dtype=np.uint8)
+        check(self.lib.cc2017_samples_host(self.ctx, m, n, u.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), count,
+                                           seed & ((1 << 64) - 1), offset, out.ctypes.data_as(C.c_void_p)), "cc2017_samples_host")
+        return out
+
+    # ------------------------------------------------------------------ measurement
+    def measure_peak(self, kind: int) -> float:
+        v = C.c_double(0)
+        check(self.lib.fock_measure_peak(self.ctx, kind, C.byref(v)), "fock_measure_peak")
+        return float(v.value)

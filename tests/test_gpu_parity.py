@@ -1,0 +1,240 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs; bit-exact for ranks / states / samples, 1e-10 relative for amplitudes and probabilities,
+sum(p) = 1 within 1e-12 (the tolerances BASELINE.json's north_star states)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import perceval_b200 as pb
+from perceval_b200.engine import FockEngine
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return FockEngine.get(0)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+# ---------------------------------------------------------------- rank / unrank: bit exact
+
+@pytest.mark.parametrize("m,n", [(1, 0), (1, 3), (2, 5), (3, 2), (4, 5), (6, 4), (12, 6), (16, 8), (5, 0), (2, 13)])
+def test_rank_unrank_device(eng, oracle, m, n):
+    N = oracle.count(m, n)
+    states = eng.enumerate(m, n).cpu().numpy()
+    ref = oracle.enumerate_states(m, n) if N <= 200000 else oracle.unrank_batch(m, n, np.arange(N, dtype=np.uint64))
+    assert (states == ref).all()
+    ranks = eng.rank(m, n, torch.from_numpy(ref)).cpu().numpy()
+    assert (ranks == np.arange(N)).all()
+
+
+def test_rank_unrank_64bit(eng, oracle):
+    m, n = 28, 14
+    N = oracle.count(m, n)
+    rng = np.random.default_rng(0)
+    ranks = np.concatenate([[0, 1, N - 1, 2 ** 32 + 12345, 12033222880], rng.integers(0, N, 5000)]).astype(np.int64)
+    st = eng.unrank(m, n, torch.from_numpy(ranks)).cpu().numpy()
+    assert (st == oracle.unrank_batch(m, n, ranks.astype(np.uint64))).all()
+    assert (eng.rank(m, n, torch.from_numpy(st)).cpu().numpy() == ranks).all()
+    # mismatch in photon number -> npos (-1 as int64)
+    bad = st.copy()
+    bad[0, 0] += 1
+    assert eng.rank(m, n, torch.from_numpy(bad)).cpu().numpy()[0] == -1
+
+
+# ---------------------------------------------------------------- SLOS
+
+@pytest.mark.parametrize("m,in_state", [(2, (1, 1)), (2, (2, 3)), (2, (8, 5)), (6, (1, 0, 1, 1, 0, 1)), (6, (0, 3, 0, 1, 1, 0)),
+                                        (12, (1,) * 6 + (0,) * 6), (12, (2, 2, 1, 1) + (0,) * 8), (16, (1,) * 8 + (0,) * 8),
+                                        (3, (0, 0, 4)), (1, (3,)), (5, (0, 0, 0, 0, 0)), (20, (1,) * 5 + (0,) * 15)])
+def test_slos_distribution_vs_oracle(eng, oracle, m, in_state):
+    u = oracle.random_unitary(m, seed=3)
+    U = eng.unitary(u)
+    probs, psum, coefs = eng.slos_probs(U, in_state, want_coefs=True)
+    ref_c = oracle.slos_coefs(u, in_state)
+    ref_p = oracle.slos_probs(u, in_state)
+    assert rel_err(coefs.cpu().numpy(), ref_c) < REL
+    assert rel_err(probs.cpu().numpy(), ref_p) < REL
+    assert abs(float(psum.item()) - 1.0) < 1e-12
+    assert abs(probs.sum().item() - 1.0) < 1e-12
+    # probs-only path (no coefficient write) is the same numbers
+    p2, s2, c2 = eng.slos_probs(U, in_state, want_coefs=False)
+    assert c2 is None and torch.equal(p2, probs)
+    # stand-alone epilogues
+    n = sum(in_state)
+    p3, s3 = eng.slos_probs_from_coefs(m, n, coefs, oracle.prodnfact(in_state))
+    assert torch.equal(p3, probs)
+    amps = eng.slos_amplitudes_from_coefs(m, n, coefs, oracle.prodnfact(in_state)).cpu().numpy()
+    assert rel_err(amps, oracle.slos_amplitudes(u, in_state)) < REL
+    # host-buffer entry point
+    ph, sh = eng.slos_probs_host(u, in_state)
+    assert (ph == probs.cpu().numpy()).all() and abs(sh - 1) < 1e-12
+
+
+def test_slos_single_layer_vs_literal_reference_loop(eng, oracle):
+    # one layer against the literal scatter loop of _slos.py:91-97, every input mode, partial child/parent windows
+    m, k = 5, 4
+    u = oracle.random_unitary(m, seed=11)
+    U = eng.unitary(u)
+    rng = np.random.default_rng(5)
+    parent = rng.standard_normal(oracle.count(m, k - 1)) + 1j * rng.standard_normal(oracle.count(m, k - 1))
+    P = torch.from_numpy(parent).cuda()
+    for mk in range(m):
+        ref = oracle.slos_layer(m, k, u, mk, parent, scatter=True)
+        got = eng.slos_layer(m, k, U, mk, P).cpu().numpy()
+        assert rel_err(got, ref) < 1e-13
+        lo, hi = 7, 51
+        part = eng.slos_layer(m, k, U, mk, P, child_begin=lo, child_end=hi).cpu().numpy()
+        assert (part == got[lo:hi]).all()
+    # a parent outside the resident window is flagged, not silently read
+    eng.slos_layer(m, k, U, 0, P[3:], parent_begin=3)
+    with pytest.raises(pb.FockError):
+        eng.check_status()
+    eng.check_status()  # flag cleared
+
+
+def test_slos_golden_fixture(eng):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "slos_6_12_seed0.npz"))
+    U = eng.unitary(g["u"])
+    probs, psum, _ = eng.slos_probs(U, tuple(g["in_state"]))
+    assert rel_err(probs.cpu().numpy(), g["probs"]) < REL
+
+
+@pytest.mark.parametrize("n,m", [(10, 20), (12, 24)])
+def test_slos_full_size_properties(eng, oracle, n, m):
+    # BASELINE config sizes: sum(p) = 1 and sampled amplitudes against independent Naive (Glynn) oracle values
+    u = oracle.random_unitary(m, seed=0)
+    U = eng.unitary(u)
+    in_state = (1,) * n + (0,) * (m - n)
+    probs, psum, _ = eng.slos_probs(U, in_state)
+    assert abs(float(psum.item()) - 1.0) < 1e-12
+    N = oracle.count(m, n)
+    rng = np.random.default_rng(1)
+    ranks = np.concatenate([[0, N - 1], rng.integers(0, N, 14)]).astype(np.uint64)
+    states = oracle.unrank_batch(m, n, ranks)
+    got = probs[torch.from_numpy(ranks.astype(np.int64)).cuda()].cpu().numpy()
+    for st, p in zip(states, got):
+        ref = abs(oracle.naive_amplitude(u, in_state, st)) ** 2
+        assert abs(p - ref) <= REL * max(ref, 1e-30) + 1e-24
+    del probs
+    torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------- permanents / Naive
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 16, 19, 20, 22])
+def test_permanents_vs_oracle(eng, oracle, n):
+    rng = np.random.default_rng(n)
+    B = 5 if n < 16 else 2
+    mats = rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))
+    got = eng.permanents(torch.from_numpy(mats)).cpu().numpy() if n > 0 else None
+    if n == 0:
+        got = eng.permanents(torch.zeros((3, 0, 0), dtype=torch.complex128)).cpu().numpy()
+        assert (got == 1).all()
+        return
+    ref = np.array([oracle.permanent(mats[b]) for b in range(B)])
+    assert np.abs(got - ref).max() <= REL * np.abs(ref).max()
+    assert (eng.permanents_host(mats) == got).all()
+    if n >= 3:  # Gray-range split (multi-GPU partition) sums to the whole
+        G = 1 << (n - 1)
+        cut = G // 3
+        a = eng.permanents(torch.from_numpy(mats), 0, cut).cpu().numpy()
+        b = eng.permanents(torch.from_numpy(mats), cut, G).cpu().numpy()
+        assert np.abs(a + b - ref).max() <= REL * np.abs(ref).max()
+
+
+def test_many_small_permanents(eng, oracle):
+    rng = np.random.default_rng(9)
+    for n in [2, 4, 6, 9]:
+        mats = rng.standard_normal((3000, n, n)) + 1j * rng.standard_normal((3000, n, n))
+        got = eng.permanents(torch.from_numpy(mats)).cpu().numpy()
+        ref = np.array([oracle.permanent(mats[b]) for b in range(0, 3000, 97)])
+        assert np.abs(got[::97] - ref).max() <= REL * np.abs(ref).max()
+
+
+def test_permanent_haar_submatrix_n24(eng, oracle):
+    # BASELINE config 2 shape: top-left n x n block of a Haar 2n x 2n unitary
+    n = 24
+    u = oracle.random_unitary(2 * n, seed=1)
+    mat = np.ascontiguousarray(u[:n, :n])
+    got = complex(eng.permanents(torch.from_numpy(mat[None])).cpu().numpy()[0])
+    ref = oracle.permanent(mat)
+    assert abs(got - ref) <= REL * abs(ref)
+
+
+@pytest.mark.parametrize("m,in_state", [(6, (1, 0, 1, 1, 0, 1)), (5, (2, 0, 1, 0, 3)), (4, (0, 1, 0, 0)), (8, (1,) * 8)])
+def test_naive_amplitudes_vs_oracle(eng, oracle, m, in_state):
+    u = oracle.random_unitary(m, seed=4)
+    U = eng.unitary(u)
+    n = sum(in_state)
+    N = oracle.count(m, n)
+    amps = eng.naive_amplitudes(U, in_state, out_ranks=torch.arange(N)).cpu().numpy()
+    states = oracle.enumerate_states(m, n)
+    ref = np.array([oracle.naive_amplitude(u, in_state, s) for s in states])
+    assert rel_err(amps, ref) < REL
+    amps2 = eng.naive_amplitudes(U, in_state, out_states=torch.from_numpy(states)).cpu().numpy()
+    assert (amps2 == amps).all()
+    # SLOS == Naive on the device as well
+    probs, _, _ = eng.slos_probs(U, in_state)
+    assert rel_err(np.abs(amps) ** 2, probs.cpu().numpy()) < 1e-9
+
+
+# ---------------------------------------------------------------- Clifford & Clifford sampler
+
+@pytest.mark.parametrize("m,in_state,count", [(2, (0, 1), 512), (4, (1, 1, 1, 0), 2000), (4, (2, 1, 0, 0), 2000),
+                                              (8, (1, 1, 1, 1, 0, 0, 0, 0), 1500), (12, (1,) * 6 + (0,) * 6, 1000),
+                                              (30, (1,) * 10 + (0,) * 20, 300), (7, (0, 3, 0, 2, 0, 0, 1), 500),
+                                              (40, (1,) * 13 + (0,) * 27, 64), (3, (0, 0, 0), 10)])
+def test_cc2017_samples_bit_exact_vs_oracle(eng, oracle, m, in_state, count):
+    u = oracle.random_unitary(m, seed=8)
+    U = eng.unitary(u)
+    got = eng.cc2017_samples(U, in_state, count, seed=1234, offset=17).cpu().numpy()
+    ref = oracle.cc2017_samples(u, in_state, count, seed=1234, offset=17)
+    assert (got.sum(axis=1) == sum(in_state)).all()          # photon number conserved: support inside FSArray(m, n)
+    mismatch = (got != ref).any(axis=1).mean()
+    assert mismatch <= 2e-3, mismatch                          # identical draws; only round-off at a CDF edge may differ
+    # the stream does not depend on how the batch is split
+    a = eng.cc2017_samples(U, in_state, count // 2, seed=1234, offset=17).cpu().numpy()
+    b = eng.cc2017_samples(U, in_state, count - count // 2, seed=1234, offset=17 + count // 2).cpu().numpy()
+    assert (np.concatenate([a, b]) == got).all()
+    assert (eng.cc2017_samples_host(u, in_state, count, seed=1234, offset=17) == got).all()
+
+
+def test_cc2017_distribution_matches_slos(eng, oracle):
+    m, in_state, count = 6, (1, 1, 0, 1, 0, 1), 200000
+    n = sum(in_state)
+    u = oracle.random_unitary(m, seed=21)
+    U = eng.unitary(u)
+    smp = eng.cc2017_samples(U, in_state, count, seed=7)
+    ranks = eng.rank(m, n, smp).cpu().numpy()
+    N = oracle.count(m, n)
+    freq = np.bincount(ranks, minlength=N) / count
+    p = oracle.slos_probs(u, in_state)
+    tvd = 0.5 * np.abs(freq - p).sum()
+    assert tvd < 0.02, tvd
+    chi2 = (((freq - p) * count) ** 2 / np.maximum(p * count, 1e-9))[p * count > 5].sum()
+    dof = (p * count > 5).sum()
+    assert chi2 < dof + 6 * math.sqrt(2 * dof), (chi2, dof)
+
+
+def test_cc2017_hom_support(eng, oracle):
+    # tests/components/test_processor.py:130-162: no |1,1> through a balanced beam splitter
+    U = eng.unitary(oracle.bs_rx())
+    smp = eng.cc2017_samples(U, (1, 1), 500, seed=3).cpu().numpy()
+    assert not ((smp[:, 0] == 1) & (smp[:, 1] == 1)).any()
+    # tests/backends/test_backends.py:58-67
+    U = eng.unitary(oracle.bs_h())
+    smp = eng.cc2017_samples(U, (0, 1), 10000, seed=5).cpu().numpy()
+    c01 = ((smp[:, 0] == 0) & (smp[:, 1] == 1)).sum()
+    assert 4750 < c01 < 5250 and c01 + ((smp[:, 0] == 1) & (smp[:, 1] == 0)).sum() == 10000
