@@ -12,6 +12,8 @@
 //     rank_{k-1}(s - e_j) = rank_k(s) - E_j(s),   E_j = sum_{i<j} Dt[q_i][T_i],   Dt[q][T] = Bt[q][T]-Bt[q][T-1]
 // so one walk over the modes un-ranks the child AND yields every parent rank with one shared-memory look-up per
 // mode.  Bt/Dt (binomials), the U column and the factorial table are staged in shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define SLOS_BLOCK 256
@@ -164,6 +166,255 @@ __global__ void __launch_bounds__(SLOS_BLOCK) slos_epilogue_kernel(int m, int n,
     }
 }
 
+
+// ================================================================================================================
+// Tile kernel (v2): prefix-uniform formulation.
+//
+// Split the m modes into a PREFIX (first p = m - D modes) and a TAIL (last D modes).  All children that share the prefix
+// pi (weight w) form one contiguous rank range ("tile") [base(pi), base(pi) + S), S = C(u + D - 1, u), u = k - w, in
+// which the local index t is the rank of the tail inside FS(D, u).  For every child of the tile
+//     parent rank for a prefix mode j (pi_j > 0)  =  (base - E_j) + t          -> aligned, perfectly coalesced row
+//     parent rank for a tail mode   j (tau_j > 0) =  (base - E_p) + (t - tailE_j(tau))   -> gather inside one small block
+// with E_j = sum_{i<j} Dt[m-1-i][T_i] depending on the prefix only, and tailE_j depending on (u, t) only.
+// A CTA therefore fixes (w, a chunk of 256 tail indices) once -- each thread un-ranks ITS tail a single time and keeps
+// the <= D tail parent offsets and U entries in registers -- and then sweeps hundreds of prefixes: per prefix the only
+// per-thread work is the loads, the complex FMAs and the store.  Prefix descriptors (bases, non-zero modes, prod pi_i!)
+// are un-ranked cooperatively, one prefix per thread, into shared memory and read back as broadcasts.
+// Classes with S < 256 pack G = 256 / S prefixes per sweep step so the lanes stay busy.
+// ================================================================================================================
+#define TILE_BLOCK 256
+#define TILE_DB 128   // descriptors per batch
+
+struct TileClass {
+    int w, u;
+    uint32_t S, G, nchunks, pad;
+    uint64_t rho_lo, np;      // prefix ranks [rho_lo, rho_lo + np) of FS(p, w) intersect the child range
+    uint64_t item_begin;      // first work item (CTA index) of this class
+    uint64_t per_item;        // prefixes per work item
+};
+
+struct TileArgs {
+    int m, k, mk, p, ncls, maxnz;
+    const uint64_t *bt, *dt;
+    const double2 *U;
+    const double2 *parent;
+    uint64_t pbegin, pend;
+    double2 *child;
+    double *probs;
+    double *sum;
+    double inv_in_fact;
+    uint64_t cbegin, cend;
+    int *status;
+    TileClass cls[FOCK_TMAX];
+};
+
+struct __align__(16) TileDesc {
+    uint64_t cbase, tbase;
+    double pfact;
+    int nz, pad;
+};
+
+#define TILE_VP 4   // prefix edges whose loads are issued together with the tail loads
+#define TILE_TB 8   // tail parents loaded per batch
+
+template <int D, int MODE, bool CHECK>
+__global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_constant__ TileArgs a) {
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    const int m = a.m, p = a.p, maxnz = a.maxnz;
+    const int tid = threadIdx.x;
+    uint64_t *s_bt = (uint64_t *)tile_smem;
+    uint64_t *s_dt = s_bt + m * FOCK_TMAX;
+    double2 *s_u = (double2 *)(s_dt + m * FOCK_TMAX);
+    double *s_fact = (double *)(s_u + m);
+    TileDesc *s_desc = (TileDesc *)(s_fact + 34);
+    double2 *e_u = (double2 *)(s_desc + TILE_DB);
+    uint64_t *e_pb = (uint64_t *)(e_u + TILE_DB * maxnz);
+    __shared__ double s_red[TILE_BLOCK / 32];
+
+    for (int i = tid; i < m * FOCK_TMAX; i += TILE_BLOCK) {
+        s_bt[i] = a.bt[i];
+        s_dt[i] = a.dt[i];
+    }
+    for (int i = tid; i < m; i += TILE_BLOCK) s_u[i] = a.U[(size_t)i * m + a.mk];
+    if (tid == 0) {
+        double f = 1.0;
+        s_fact[0] = 1.0;
+        for (int i = 1; i < FOCK_TMAX; ++i) { f *= (double)i; s_fact[i] = f; }
+    }
+    // ---- which class / work item
+    int ci = 0;
+    for (int c = 1; c < a.ncls; ++c)
+        if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
+    const int w = a.cls[ci].w, u = a.cls[ci].u;
+    const uint32_t S = a.cls[ci].S, G = a.cls[ci].G, nchunks = a.cls[ci].nchunks;
+    const uint64_t local = (uint64_t)blockIdx.x - a.cls[ci].item_begin;
+    const uint32_t chunk = (uint32_t)(local % nchunks);
+    const uint64_t range = local / nchunks;
+    const uint64_t rho_a = a.cls[ci].rho_lo + range * a.cls[ci].per_item;
+    uint64_t rho_b = rho_a + a.cls[ci].per_item;
+    if (rho_b > a.cls[ci].rho_lo + a.cls[ci].np) rho_b = a.cls[ci].rho_lo + a.cls[ci].np;
+    __syncthreads();
+
+    // ---- per-thread tail: un-rank t in FS(D, u) once; keep (mode, parent offset) of the non-zero tail modes, compacted
+    uint32_t g, t;
+    if (G > 1) { g = tid / S; t = tid - g * S; } else { g = 0; t = chunk * TILE_BLOCK + tid; }
+    const bool active = (g < G) && (t < S);
+    uint32_t toff[D];            // local rank of (tau - e_mode) in FS(D, u-1) for the c-th occupied tail mode
+    uint32_t tmode[(D + 5) / 6]; // the tail mode of entry c, 5 bits each, 6 per word
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < (D + 5) / 6; ++c) tmode[c] = 0;
+    double tfact = 1.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) toff[c] = 0;
+    if (active) {
+        uint64_t rem = t;
+        uint32_t E = 0;
+        int Tprev = u;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            int T = 0;
+            if (i < D - 1) {
+                const uint64_t *row = s_bt + (D - 1 - i) * FOCK_TMAX;
+                T = Tprev;
+                while (row[T] > rem) --T;
+                rem -= row[T];
+            }
+            const int si = Tprev - T;
+            if (si > 0) {
+                const uint32_t off = t - E;
+#pragma unroll
+                for (int c = 0; c < D; ++c)
+                    if (c == cnt) { toff[c] = off; tmode[c / 6] |= (uint32_t)i << (5 * (c % 6)); }
+                ++cnt;
+                tfact *= s_fact[si];
+            }
+            if (i < D - 1 && T > 0) E += (uint32_t)s_dt[(D - 1 - i) * FOCK_TMAX + T];
+            Tprev = T;
+        }
+    }
+    const int wcnt = __reduce_max_sync(0xffffffffu, cnt);   // warp-uniform trip count of the tail phase
+
+    const double2 *__restrict__ parent = a.parent - a.pbegin;
+    const double2 *__restrict__ parent_t = parent + t;
+    const double2 *s_ut = s_u + p;
+    double local_sum = 0.0;
+    bool oob = false;
+
+    for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += TILE_DB) {
+        const int nb = (int)((rho_b - rho0) < (uint64_t)TILE_DB ? (rho_b - rho0) : (uint64_t)TILE_DB);
+        __syncthreads();
+        // ---- cooperative prefix descriptors: thread i un-ranks prefix rho0 + i of FS(p, w)
+        if (tid < nb) {
+            uint64_t rem = rho0 + tid;
+            int Tprev = w;            // prefix photons still to place
+            uint64_t base = 0, E = 0;
+            int nz = 0;
+            double pf = 1.0;
+            for (int i = 0; i < p; ++i) {
+                int T = 0;
+                if (i < p - 1) {
+                    const uint64_t *row = s_bt + (p - 1 - i) * FOCK_TMAX;
+                    T = Tprev;
+                    while (row[T] > rem) --T;
+                    rem -= row[T];
+                }
+                const int si = Tprev - T;
+                const int Tfull = T + u;   // photons right of mode i in the full state
+                if (si > 0) {
+                    e_pb[tid * maxnz + nz] = E;
+                    e_u[tid * maxnz + nz] = s_u[i];
+                    ++nz;
+                    pf *= s_fact[si];
+                }
+                base += s_bt[(m - 1 - i) * FOCK_TMAX + Tfull];
+                if (Tfull > 0) E += s_dt[(m - 1 - i) * FOCK_TMAX + Tfull];
+                Tprev = T;
+            }
+            for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
+            TileDesc td;
+            td.cbase = base;
+            td.tbase = base - E;   // only meaningful (and only used) when u >= 1
+            td.pfact = pf;
+            td.nz = nz;
+            td.pad = 0;
+            s_desc[tid] = td;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int i = (int)g; i < nb; i += (int)G) {
+            const TileDesc td = s_desc[i];
+            const uint64_t r = td.cbase + t;
+            if (CHECK && (r < a.cbegin || r >= a.cend)) continue;
+            const uint64_t *pb = e_pb + i * maxnz;
+            const double2 *pu = e_u + i * maxnz;
+            const int nz = td.nz;
+            // ---- phase 1: prefix rows + first batch of tail parents: every load is issued before any arithmetic.
+            // Values of entries >= nz / >= wcnt stay undefined and are never consumed (the FMAs carry the same guards).
+            const double2 *__restrict__ tbp = parent + td.tbase;   // tail-parent block of this tile
+            double2 pv[TILE_VP], tv[TILE_TB];
+#pragma unroll
+            for (int e = 0; e < TILE_VP; ++e) {
+                if (e < nz) {
+                    if (CHECK && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; pv[e] = make_double2(0.0, 0.0); }
+                    else pv[e] = parent_t[pb[e]];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < TILE_TB && c < D; ++c) {
+                if (c < wcnt) {
+                    if (CHECK && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c] = make_double2(0.0, 0.0); }
+                    else tv[c] = tbp[toff[c]];
+                }
+            }
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int e = 0; e < TILE_VP; ++e)
+                if (e < nz) acc = cfma(pu[e], pv[e], acc);
+            for (int e = TILE_VP; e < nz; ++e) {
+                if (CHECK && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; continue; }
+                acc = cfma(pu[e], parent_t[pb[e]], acc);
+            }
+#pragma unroll
+            for (int c = 0; c < TILE_TB && c < D; ++c)
+                if (c < cnt) acc = cfma(s_ut[(tmode[c / 6] >> (5 * (c % 6))) & 31u], tv[c], acc);
+            // ---- further tail batches (only when some lane of the warp has more than TILE_TB occupied tail modes)
+#pragma unroll
+            for (int c0 = TILE_TB; c0 < D; c0 += TILE_TB) {
+                if (c0 < wcnt) {
+#pragma unroll
+                    for (int c = c0; c < c0 + TILE_TB && c < D; ++c) {
+                        if (c < wcnt) {
+                            if (CHECK && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c - c0] = make_double2(0.0, 0.0); }
+                            else tv[c - c0] = tbp[toff[c]];
+                        }
+                    }
+#pragma unroll
+                    for (int c = c0; c < c0 + TILE_TB && c < D; ++c)
+                        if (c < cnt) acc = cfma(s_ut[(tmode[c / 6] >> (5 * (c % 6))) & 31u], tv[c - c0], acc);
+                }
+            }
+            if (MODE & 1) a.child[r - a.cbegin] = acc;
+            if (MODE & 2) {
+                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
+                a.probs[r - a.cbegin] = pr;
+                local_sum += pr;
+            }
+        }
+    }
+    if (CHECK && oob && a.status) atomicExch(a.status, 1);
+    if ((MODE & 2) && a.sum) {
+        local_sum = warp_sum(local_sum);
+        if ((tid & 31) == 0) s_red[tid >> 5] = local_sum;
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < TILE_BLOCK / 32 ? s_red[tid] : 0.0;
+            v = warp_sum(v);
+            if (tid == 0) atomicAdd(a.sum, v);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static int slos_check(const char *who, fock_ctx *c, int m, int k) {
     FOCK_REQUIRE(c != nullptr, FOCK_ERR_ARG, "%s: ctx is NULL", who);
@@ -180,6 +431,119 @@ static unsigned slos_grid(fock_ctx *c, uint64_t cnt) {
     return (unsigned)(g ? g : 1);
 }
 
+// ---- host helpers for the tile kernel
+static uint64_t host_prefix_base(int m, int p, int w, int u, uint64_t rho) {
+    // child rank of (prefix #rho of FS(p, w), tail |u,0,..,0>) in FS(m, w + u)
+    const uint64_t *bt = fock_host_bt();
+    uint64_t rem = rho, base = 0;
+    int Tprev = w;
+    for (int i = 0; i < p; ++i) {
+        int T = 0;
+        if (i < p - 1) {
+            const uint64_t *row = bt + (p - 1 - i) * FOCK_TMAX;
+            T = Tprev;
+            while (row[T] > rem) --T;
+            rem -= row[T];
+        }
+        base += bt[(m - 1 - i) * FOCK_TMAX + (T + u)];
+        Tprev = T;
+    }
+    return base;
+}
+
+static int slos_tail_modes(int m) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("FOCK_SLOS_TAIL");
+        forced = e ? atoi(e) : -1;
+    }
+    // tail width: wide enough that almost every child lives in a tile of >= 256 states
+    int D = forced > 0 ? forced : (m >= 26 ? 20 : (m >= 20 ? 16 : (m >= 16 ? 12 : (m >= 12 ? 8 : (m >= 8 ? 6 : (m >= 6 ? 4 : 0))))));
+    if (D != 4 && D != 6 && D != 8 && D != 10 && D != 12 && D != 16 && D != 20) D = 0;
+    if (D > m - 1) D = 0;
+    return D;
+}
+
+template <int D>
+static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, bool check, unsigned grid, size_t smem, cudaStream_t st) {
+#define TILE_LAUNCH(MODE, CHK)                                                                                              \
+    do {                                                                                                                  \
+        FOCK_CUDA(cudaFuncSetAttribute(slos_tile_kernel<D, MODE, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        slos_tile_kernel<D, MODE, CHK><<<grid, TILE_BLOCK, smem, st>>>(a);                                                \
+    } while (0)
+    if (want_probs && want_child) { if (check) TILE_LAUNCH(3, true); else TILE_LAUNCH(3, false); }
+    else if (want_probs) { if (check) TILE_LAUNCH(2, true); else TILE_LAUNCH(2, false); }
+    else { if (check) TILE_LAUNCH(1, true); else TILE_LAUNCH(1, false); }
+#undef TILE_LAUNCH
+    c->launches++;
+    return fock_check_cuda(cudaGetLastError(), "slos_tile_kernel");
+}
+
+static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
+                            uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
+                            uint64_t ce, cudaStream_t st) {
+    const int p = m - D;
+    TileArgs a;
+    memset(&a, 0, sizeof a);
+    a.m = m; a.k = k; a.mk = mk; a.p = p;
+    a.maxnz = p < k ? p : k;
+    if (a.maxnz < 1) a.maxnz = 1;
+    a.bt = c->d_bt; a.dt = c->d_dt;
+    a.U = (const double2 *)d_U;
+    a.parent = (const double2 *)d_parent;
+    a.pbegin = pb; a.pend = pe;
+    a.child = (double2 *)d_child;
+    a.probs = d_probs;
+    a.sum = d_sum;
+    a.inv_in_fact = 1.0 / in_prodnfact;
+    a.cbegin = cb; a.cend = ce;
+    a.status = c->d_status;
+    const bool full = (cb == 0 && ce == fock_count(m, k));
+    uint64_t items = 0;
+    int ncls = 0;
+    for (int w = 0; w <= k; ++w) {
+        const int u = k - w;
+        const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
+        FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
+        uint64_t lo = 0, hi = np_total;
+        if (!full) {
+            // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
+            uint64_t l = 0, h = np_total;
+            while (l < h) { uint64_t mid = (l + h) / 2; if (host_prefix_base(m, p, w, u, mid) + S64 > cb) h = mid; else l = mid + 1; }
+            lo = l;
+            l = lo; h = np_total;
+            while (l < h) { uint64_t mid = (l + h) / 2; if (host_prefix_base(m, p, w, u, mid) >= ce) h = mid; else l = mid + 1; }
+            hi = l;
+        }
+        if (hi <= lo) continue;
+        TileClass &tc = a.cls[ncls++];
+        tc.w = w; tc.u = u;
+        tc.S = (uint32_t)S64;
+        tc.G = S64 >= TILE_BLOCK ? 1u : (uint32_t)(TILE_BLOCK / S64);
+        tc.nchunks = S64 >= TILE_BLOCK ? (uint32_t)((S64 + TILE_BLOCK - 1) / TILE_BLOCK) : 1u;
+        tc.rho_lo = lo; tc.np = hi - lo;
+        tc.per_item = 512ull * tc.G;
+        tc.item_begin = items;
+        items += ((tc.np + tc.per_item - 1) / tc.per_item) * tc.nchunks;
+    }
+    a.ncls = ncls;
+    if (items == 0) return FOCK_OK;
+    FOCK_REQUIRE(items < (1ull << 31), FOCK_ERR_LIMIT, "slos: too many work items");
+    size_t smem = (size_t)2 * m * FOCK_TMAX * 8 + (size_t)m * 16 + 34 * 8 + (size_t)TILE_DB * sizeof(TileDesc) +
+                  (size_t)TILE_DB * a.maxnz * 24 + 16;
+    const bool check = !(pb == 0 && pe == fock_count(m, k - 1)) || !full;
+    const bool wc = d_child != nullptr, wp = d_probs != nullptr;
+    switch (D) {
+        case 4: return launch_tile<4>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        case 6: return launch_tile<6>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        case 8: return launch_tile<8>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        case 10: return launch_tile<10>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        case 12: return launch_tile<12>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        case 16: return launch_tile<16>(c, a, wc, wp, check, (unsigned)items, smem, st);
+        default: return launch_tile<20>(c, a, wc, wp, check, (unsigned)items, smem, st);
+    }
+}
+
 static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                            uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
                            uint64_t ce, void *stream, const char *who) {
@@ -192,6 +556,13 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     FOCK_REQUIRE(d_child || d_probs, FOCK_ERR_ARG, "%s: no output buffer", who);
     if (cb == ce) return FOCK_OK;
     ScopedDevice sd(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // large layers: tile kernel; small layers / few modes: the per-child gather kernel
+    static int force_v1 = -1;
+    if (force_v1 < 0) { const char *e = getenv("FOCK_SLOS_KERNEL"); force_v1 = (e && !strcmp(e, "v1")) ? 1 : 0; }
+    const int D = slos_tail_modes(m);
+    if (!force_v1 && D > 0 && (ce - cb) >= 32768)
+        return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st);
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
     a.bt = c->d_bt; a.dt = c->d_dt;
@@ -205,7 +576,6 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     a.cbegin = cb; a.cend = ce;
     a.status = c->d_status;
     unsigned grid = slos_grid(c, ce - cb);
-    cudaStream_t st = (cudaStream_t)stream;
     if (d_probs && d_child) slos_layer_gather_kernel<3><<<grid, SLOS_BLOCK, 0, st>>>(a);
     else if (d_probs) slos_layer_gather_kernel<2><<<grid, SLOS_BLOCK, 0, st>>>(a);
     else slos_layer_gather_kernel<1><<<grid, SLOS_BLOCK, 0, st>>>(a);

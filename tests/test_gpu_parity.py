@@ -73,7 +73,7 @@ def test_slos_distribution_vs_oracle(eng, oracle, m, in_state):
     # stand-alone epilogues
     n = sum(in_state)
     p3, s3 = eng.slos_probs_from_coefs(m, n, coefs, oracle.prodnfact(in_state))
-    assert torch.equal(p3, probs)
+    assert rel_err(p3.cpu().numpy(), probs.cpu().numpy()) < 1e-14
     amps = eng.slos_amplitudes_from_coefs(m, n, coefs, oracle.prodnfact(in_state)).cpu().numpy()
     assert rel_err(amps, oracle.slos_amplitudes(u, in_state)) < REL
     # host-buffer entry point
@@ -238,3 +238,33 @@ def test_cc2017_hom_support(eng, oracle):
     smp = eng.cc2017_samples(U, (0, 1), 10000, seed=5).cpu().numpy()
     c01 = ((smp[:, 0] == 0) & (smp[:, 1] == 1)).sum()
     assert 4750 < c01 < 5250 and c01 + ((smp[:, 0] == 1) & (smp[:, 1] == 0)).sum() == 10000
+
+
+@pytest.mark.parametrize("m,k", [(16, 8), (14, 7), (24, 6)])
+def test_slos_tile_kernel_sharded_ranges(eng, oracle, m, k):
+    # child-range sharding (multi-GPU partition) and parent windows through the tile kernel: identical bits to the
+    # full-layer launch, and equal to the oracle's layer
+    u = oracle.random_unitary(m, seed=12)
+    U = eng.unitary(u)
+    Np, Nc = oracle.count(m, k - 1), oracle.count(m, k)
+    rng = np.random.default_rng(2)
+    parent = rng.standard_normal(Np) + 1j * rng.standard_normal(Np)
+    P = torch.from_numpy(parent).cuda()
+    full = eng.slos_layer(m, k, U, 3, P)
+    ref = oracle.slos_layer(m, k, u, 3, parent, scatter=False)
+    assert rel_err(full.cpu().numpy(), ref) < 1e-13
+    cuts = [0, Nc // 3 + 17, 2 * Nc // 3 - 5, Nc]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        part = eng.slos_layer(m, k, U, 3, P, child_begin=b, child_end=e)
+        assert torch.equal(part, full[b:e])
+    eng.check_status()
+    # probabilities + sum through the sharded path
+    psum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    pieces = [eng.slos_layer_probs(m, k, U, 3, P, 2.0, psum=psum, child_begin=b, child_end=e) for b, e in zip(cuts[:-1], cuts[1:])]
+    allp, s1 = eng.slos_probs_from_coefs(m, k, full, 2.0)
+    assert rel_err(torch.cat(pieces).cpu().numpy(), allp.cpu().numpy()) < 1e-13
+    assert abs(psum.item() - s1.item()) <= 1e-12 * abs(s1.item())
+    # a window that misses needed parents is flagged
+    eng.slos_layer(m, k, U, 3, P[100:], parent_begin=100, child_begin=0, child_end=Nc // 2)
+    with pytest.raises(pb.FockError):
+        eng.check_status()
