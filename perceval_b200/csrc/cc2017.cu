@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(CC_BLOCK) cc2017_kernel(const CcArgs a) {
     // per-warp shared layout
     const size_t bytes_B = (size_t)(n > 1 ? n - 1 : 1) * NP * sizeof(double2);
     const size_t bytes_sp = NP * sizeof(double2);
-    const size_t bytes_w = (size_t)m * sizeof(double);
+    const size_t bytes_w = (((size_t)m * sizeof(double)) + 15) & ~(size_t)15;
     const size_t bytes_i = 2 * FOCK_NMAX * sizeof(int);
     const size_t per_warp = bytes_B + bytes_sp + bytes_w + bytes_i;
     unsigned char *base = smem_raw + warp * per_warp;
@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(CC_BLOCK) cc2017_kernel(const CcArgs a) {
                 const uint64_t C = (uint64_t)1 << (r - 1);
                 const uint64_t per = C >= 8 ? (C >> 3) : 1;
                 const uint64_t g0 = (uint64_t)grp * per;
-                const uint64_t g1 = g0 + per;
                 const bool active = g0 < C;
                 double2 v[H], acc[H], suf[H];
 #pragma unroll
@@ -232,7 +231,7 @@ static thread_local CcScratch g_cc;
 template <int H>
 static int launch_cc(fock_ctx *c, const CcArgs &a, cudaStream_t st) {
     const int NP = 4 * H;
-    const size_t per_warp = (size_t)(a.n > 1 ? a.n - 1 : 1) * NP * 16 + (size_t)NP * 16 + (size_t)a.m * 8 + 2 * FOCK_NMAX * sizeof(int);
+    const size_t per_warp = (size_t)(a.n > 1 ? a.n - 1 : 1) * NP * 16 + (size_t)NP * 16 + ((((size_t)a.m * 8) + 15) & ~(size_t)15) + 2 * FOCK_NMAX * sizeof(int);
     const size_t smem = per_warp * CC_WARPS;
     FOCK_REQUIRE(smem <= 220 * 1024, FOCK_ERR_LIMIT, "cc2017_samples: m=%d, n=%d needs %zu B of shared memory per CTA", a.m, a.n, smem);
     FOCK_CUDA(cudaFuncSetAttribute(cc2017_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,105 @@
+"""CPU, world_size 2, gloo: the multi-GPU partition / exchange logic of perceval_b200.dist with the compute step
+injected from the CPU oracle (the product's device kernels need a GPU; the N>1 plumbing does not)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, exchange, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from perceval_b200 import dist as pdist
+
+    m, in_state = 7, (1, 1, 0, 1, 1, 0, 1)
+    n = sum(in_state)
+    u = oracle.random_unitary(m, seed=4)
+    order = oracle.slos_order(in_state)
+    lib = oracle.lib()
+
+    def layer_fn(k, mk, parent, b, e):
+        parent_np = np.ones(1, dtype=np.complex128) if parent is None else parent.numpy()
+        child = np.empty(e - b, dtype=np.complex128)
+        lib.orc_slos_layer_gather(m, k, oracle._p(oracle._u(u)), mk, oracle._p(np.ascontiguousarray(parent_np)), oracle._p(child), b, e)
+        return torch.from_numpy(child)
+
+    def last_fn(k, mk, parent, b, e):
+        c = layer_fn(k, mk, parent, b, e).numpy()
+        states = oracle.unrank_batch(m, k, np.arange(b, e, dtype=np.uint64))
+        f = np.array([oracle.prodnfact(s) for s in states])
+        p = (np.abs(c) ** 2) * f / oracle.prodnfact(in_state)
+        return torch.from_numpy(p), torch.tensor([p.sum()], dtype=torch.float64)
+
+    probs, (b, e), psum, decisions = pdist.slos_probs_sharded(m, in_state, order, oracle.count, layer_fn, last_fn, exchange=exchange)
+    ref = oracle.slos_probs(u, in_state)
+    assert np.abs(probs.numpy() - ref[b:e]).max() < 1e-14
+    assert abs(psum.item() - 1) < 1e-12
+    assert all(d == exchange for d in decisions) or exchange == "auto"
+
+    # permanents: batch split (B >= world) and Gray-range split (B < world)
+    rng = np.random.default_rng(0)
+    mats = torch.from_numpy(rng.standard_normal((5, 6, 6)) + 1j * rng.standard_normal((5, 6, 6)))
+
+    def perm_fn(ms, g0, g1):
+        return torch.tensor([oracle.permanent(x.numpy(), g0, g1) if g1 else oracle.permanent(x.numpy()) for x in ms], dtype=torch.complex128)
+
+    want = perm_fn(mats, 0, 0)
+    got = pdist.permanents_sharded(perm_fn, mats)
+    assert torch.allclose(got, want, rtol=1e-12, atol=0)
+    got1 = pdist.permanents_sharded(perm_fn, mats[:1])
+    assert torch.allclose(got1, want[:1], rtol=1e-12, atol=0)
+
+    # sampling: disjoint index ranges + gather == the single-process stream
+    def sample_fn(cnt, off):
+        return torch.from_numpy(oracle.cc2017_samples(u, in_state, cnt, seed=11, offset=off))
+
+    for count in (64, 37):
+        allsmp = pdist.samples_sharded(sample_fn, count, offset=5)
+        assert (allsmp.numpy() == oracle.cc2017_samples(u, in_state, count, seed=11, offset=5)).all()
+    # ragged all-gather helper
+    tot = 11
+    bb, ee = pdist.shard_range(tot, rank, world)
+    full = pdist.all_gather_ragged(torch.arange(bb, ee, dtype=torch.float64), tot)
+    assert torch.equal(full, torch.arange(tot, dtype=torch.float64))
+    open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["allgather", "replicate"])
+def test_sharded_paths_world2(tmp_path, exchange):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), exchange, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_shard_range_and_exchange_model():
+    sys.path.insert(0, ROOT)
+    from perceval_b200 import dist as pdist
+    for total in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [pdist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert pdist.choose_exchange(10, 30, 1) == "replicate"
+    assert pdist.choose_exchange(286097760, 834451800, 8) in ("replicate", "allgather")
