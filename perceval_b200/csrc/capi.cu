@@ -91,6 +91,7 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     c->cc_minor = prop.minor;
     c->total_mem = prop.totalGlobalMem;
     c->launches = 0;
+    c->blk_state = nullptr;
     size_t tb = sizeof(uint64_t) * FOCK_QMAX * FOCK_TMAX;
     FOCK_CUDA(cudaMalloc(&c->d_bt, tb));
     FOCK_CUDA(cudaMalloc(&c->d_dt, tb));
@@ -103,9 +104,12 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     return FOCK_OK;
 }
 
+void slos_blk_destroy(fock_ctx *c);   // slos_blk.cu
+
 extern "C" int fock_destroy(fock_ctx *c) {
     if (!c) return FOCK_OK;
     ScopedDevice sd(c->device);
+    slos_blk_destroy(c);
     cudaFree(c->d_bt);
     cudaFree(c->d_dt);
     cudaFree(c->d_status);

@@ -21,6 +21,7 @@ struct fock_ctx {
     int *d_status;    // device-side error flag
     double *d_scratch; // small scratch (sum accumulators)
     uint64_t launches;
+    void *blk_state;   // owned by slos_blk.cu (column tables, cached layer plans)
 };
 
 void fock_set_error(const char *fmt, ...);
@@ -76,6 +77,8 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p) {
 __device__ __forceinline__ void st_stream(double2 *p, double2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- Philox4x32-10 (same keying as oracle/fock_oracle.c)
 __host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_hi, uint64_t ctr_lo, uint32_t out[4]) {

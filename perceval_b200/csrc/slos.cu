@@ -18,6 +18,11 @@
 
 #define SLOS_BLOCK 256
 
+static int slos_env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 struct SlosArgs {
     int m, k, mk;
     const uint64_t *bt, *dt;
@@ -205,6 +210,7 @@ struct TileArgs {
     double inv_in_fact;
     uint64_t cbegin, cend;
     int *status;
+    int pf;                    // prefetch distance in sweep steps (0 = off)
     TileClass cls[FOCK_TMAX];
 };
 
@@ -219,6 +225,7 @@ struct __align__(16) TileDesc {
 
 template <int D, int MODE, bool CHECK>
 __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_constant__ TileArgs a) {
+    const int PF = a.pf;
     extern __shared__ __align__(16) unsigned char tile_smem[];
     const int m = a.m, p = a.p, maxnz = a.maxnz;
     const int tid = threadIdx.x;
@@ -345,6 +352,20 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
         for (int i = (int)g; i < nb; i += (int)G) {
             const TileDesc td = s_desc[i];
             const uint64_t r = td.cbase + t;
+            if (!CHECK && PF > 0) {
+                // software prefetch into L2 of everything prefix i + PF*G will read: hides the HBM latency without
+                // spending registers on loads in flight
+                const int ip = i + PF * (int)G;
+                if (ip < nb) {
+                    const TileDesc tp = s_desc[ip];
+                    const uint64_t *pbp = e_pb + ip * maxnz;
+                    for (int e = 0; e < tp.nz; ++e) prefetch_l2(parent_t + pbp[e]);
+                    const double2 *tbn = parent + tp.tbase;
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        if (c < cnt) prefetch_l2(tbn + toff[c]);
+                }
+            }
             if (CHECK && (r < a.cbegin || r >= a.cend)) continue;
             const uint64_t *pb = e_pb + i * maxnz;
             const double2 *pu = e_u + i * maxnz;
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
             if (MODE & 1) a.child[r - a.cbegin] = acc;
             if (MODE & 2) {
                 const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
-                a.probs[r - a.cbegin] = pr;
+                __stcs(a.probs + (r - a.cbegin), pr);   // never re-read on the device: keep it out of L2's way
                 local_sum += pr;
             }
         }
@@ -416,6 +437,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------- host side
+int slos_blk_tail_modes(int m);                 // slos_blk.cu
+int slos_blk_u_limit(fock_ctx *c, int D, int k);
+int slos_layer_blocks(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, double *d_child,
+                      double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb, uint64_t ce, cudaStream_t st);
+
 static int slos_check(const char *who, fock_ctx *c, int m, int k) {
     FOCK_REQUIRE(c != nullptr, FOCK_ERR_ARG, "%s: ctx is NULL", who);
     FOCK_REQUIRE(m >= 1 && m <= FOCK_QMAX, FOCK_ERR_LIMIT, "%s: m=%d outside [1,%d]", who, m, FOCK_QMAX);
@@ -432,7 +458,9 @@ static unsigned slos_grid(fock_ctx *c, uint64_t cnt) {
 }
 
 // ---- host helpers for the tile kernel
-static uint64_t host_prefix_base(int m, int p, int w, int u, uint64_t rho) {
+uint64_t slos_host_prefix_base(int m, int p, int w, int u, uint64_t rho);
+static uint64_t host_prefix_base(int m, int p, int w, int u, uint64_t rho) { return slos_host_prefix_base(m, p, w, u, rho); }
+uint64_t slos_host_prefix_base(int m, int p, int w, int u, uint64_t rho) {
     // child rank of (prefix #rho of FS(p, w), tail |u,0,..,0>) in FS(m, w + u)
     const uint64_t *bt = fock_host_bt();
     uint64_t rem = rho, base = 0;
@@ -481,7 +509,7 @@ static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
 
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
-                            uint64_t ce, cudaStream_t st) {
+                            uint64_t ce, cudaStream_t st, int u_from = 0) {
     const int p = m - D;
     TileArgs a;
     memset(&a, 0, sizeof a);
@@ -498,11 +526,13 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     a.inv_in_fact = 1.0 / in_prodnfact;
     a.cbegin = cb; a.cend = ce;
     a.status = c->d_status;
+    a.pf = slos_env_int("FOCK_TILE_PF", 0);   // measured: +14 % time at 12/24 (issue-bound), kept as an experiment knob
     const bool full = (cb == 0 && ce == fock_count(m, k));
     uint64_t items = 0;
     int ncls = 0;
     for (int w = 0; w <= k; ++w) {
         const int u = k - w;
+        if (u < u_from) continue;   // classes below u_from are handled by the block-staged kernel (slos_blk.cu)
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
         uint64_t lo = 0, hi = np_total;
@@ -522,7 +552,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         tc.G = S64 >= TILE_BLOCK ? 1u : (uint32_t)(TILE_BLOCK / S64);
         tc.nchunks = S64 >= TILE_BLOCK ? (uint32_t)((S64 + TILE_BLOCK - 1) / TILE_BLOCK) : 1u;
         tc.rho_lo = lo; tc.np = hi - lo;
-        tc.per_item = 512ull * tc.G;
+        tc.per_item = (uint64_t)slos_env_int("FOCK_TILE_PERITEM", 512) * tc.G;
         tc.item_begin = items;
         items += ((tc.np + tc.per_item - 1) / tc.per_item) * tc.nchunks;
     }
@@ -557,12 +587,27 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     if (cb == ce) return FOCK_OK;
     ScopedDevice sd(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // large layers: tile kernel; small layers / few modes: the per-child gather kernel
-    static int force_v1 = -1;
-    if (force_v1 < 0) { const char *e = getenv("FOCK_SLOS_KERNEL"); force_v1 = (e && !strcmp(e, "v1")) ? 1 : 0; }
-    const int D = slos_tail_modes(m);
-    if (!force_v1 && D > 0 && (ce - cb) >= 32768)
-        return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st);
+    // large layers: block-staged kernel (v3, slos_blk.cu) when the whole parent layer is resident, else the tile kernel
+    // (v2); small layers / few modes: the per-child gather kernel (v1)
+    static int force = -1;
+    if (force < 0) {
+        const char *e = getenv("FOCK_SLOS_KERNEL");
+        force = (e && !strcmp(e, "v1")) ? 1 : ((e && !strcmp(e, "v3")) ? 0 : 2);
+    }
+    if (force != 1 && (ce - cb) >= 32768) {
+        const int Db = slos_blk_tail_modes(m);
+        const bool parent_full = (pb == 0 && pe == fock_count(m, k - 1));
+        if (force == 0 && Db > 0 && parent_full && ((uintptr_t)d_parent & 15) == 0) {
+            const int u_lim = slos_blk_u_limit(c, Db, k);
+            FOCK_REQUIRE(u_lim > 0, FOCK_ERR_CUDA, "slos: could not build the tail tables");
+            if (int rc = slos_layer_blocks(c, Db, m, k, d_U, mk, d_parent, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st)) return rc;
+            if (u_lim <= k)
+                return slos_layer_tiles(c, Db, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, u_lim);
+            return FOCK_OK;
+        }
+        const int D = slos_tail_modes(m);
+        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st);
+    }
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
     a.bt = c->d_bt; a.dt = c->d_dt;
