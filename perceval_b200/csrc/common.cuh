@@ -79,6 +79,10 @@ __device__ __forceinline__ void st_stream(double2 *p, double2 v) {
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// contiguous range -> L2 in one instruction (bytes: multiple of 16, 16-byte aligned address)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // ---------------------------------------------------------------- Philox4x32-10 (same keying as oracle/fock_oracle.c)
 __host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_hi, uint64_t ctr_lo, uint32_t out[4]) {

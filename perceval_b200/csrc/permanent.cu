@@ -17,6 +17,12 @@
 
 #define GLYNN_BLOCK 128
 
+#include <stdlib.h>
+static int glynn_env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 template <int N, bool SMEM>
 __device__ __forceinline__ double2 glynn_chunk(const double2 *__restrict__ M, uint64_t g0, uint64_t g1) {
     double2 v[N];
@@ -165,7 +171,8 @@ template <int N>
 static int launch_glynn(fock_ctx *c, const double2 *mats, uint64_t B, double2 *out, uint64_t g0, uint64_t g1, cudaStream_t st) {
     const uint64_t G = g1 - g0;
     const double scale = ldexp(1.0, 1 - N);
-    const uint64_t target_threads = (uint64_t)c->sm_count * 3 * GLYNN_BLOCK * 4;  // ~4 waves of 3 CTAs / SM
+    // >= ~24 waves of 3 CTAs / SM: a 4-5 wave grid loses ~12 % to the partial last wave (ncu: 4.61 waves at n=30, B=8)
+    const uint64_t target_threads = (uint64_t)c->sm_count * 3 * GLYNN_BLOCK * (uint64_t)glynn_env_int("FOCK_GLYNN_WAVES", 24);
     if (G * B <= 4096 * B && (G <= 4096) && B >= 1024) {
         // many small permanents
         uint64_t g = (B + GLYNN_BLOCK - 1) / GLYNN_BLOCK;
