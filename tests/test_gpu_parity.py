@@ -268,3 +268,41 @@ def test_slos_tile_kernel_sharded_ranges(eng, oracle, m, k):
     eng.slos_layer(m, k, U, 3, P[100:], parent_begin=100, child_begin=0, child_end=Nc // 2)
     with pytest.raises(pb.FockError):
         eng.check_status()
+
+
+# ---------------------------------------------------------------- experimental SLOS kernels (selected by environment variable)
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import oracle
+from perceval_b200.engine import FockEngine
+eng = FockEngine.get(0)
+worst = 0.0
+for m, st in [(16, (1,) * 8 + (0,) * 8), (14, (3, 2, 1, 1) + (0,) * 10), (20, (1,) * 6 + (0,) * 14)]:
+    u = oracle.random_unitary(m, seed=7)
+    U = eng.unitary(u)
+    probs, psum, coefs = eng.slos_probs(U, st, want_coefs=True)
+    ref_c, ref_p = oracle.slos_coefs(u, st), oracle.slos_probs(u, st)
+    worst = max(worst, np.abs(coefs.cpu().numpy() - ref_c).max() / np.abs(ref_c).max(),
+                np.abs(probs.cpu().numpy() - ref_p).max() / ref_p.max(), abs(float(psum.item()) - 1.0))
+eng.check_status()
+print("WORST", worst)
+"""
+
+
+@pytest.mark.parametrize("env", [{"FOCK_SLOS_KERNEL": "v1"}, {"FOCK_SLOS_KERNEL": "v3"}, {"FOCK_TILE_PIPE": "1"},
+                                 {"FOCK_TILE_LEAN": "1"}, {"FOCK_SLOS_TAIL": "8"}])
+def test_slos_kernel_variants_vs_oracle(env):
+    # every kernel variant profiles/README.md quotes is held to the same 1e-10 bar as the default (the variant is chosen
+    # once per process, hence the subprocess)
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float(out.stdout.strip().split("WORST")[-1])
+    assert worst < REL, (env, worst)
