@@ -92,6 +92,7 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     c->total_mem = prop.totalGlobalMem;
     c->launches = 0;
     c->blk_state = nullptr;
+    c->mu_state = nullptr;
     size_t tb = sizeof(uint64_t) * FOCK_QMAX * FOCK_TMAX;
     FOCK_CUDA(cudaMalloc(&c->d_bt, tb));
     FOCK_CUDA(cudaMalloc(&c->d_dt, tb));
@@ -105,11 +106,13 @@ extern "C" int fock_create(int device, fock_ctx **out) {
 }
 
 void slos_blk_destroy(fock_ctx *c);   // slos_blk.cu
+void slos_mu_destroy(fock_ctx *c);
 
 extern "C" int fock_destroy(fock_ctx *c) {
     if (!c) return FOCK_OK;
     ScopedDevice sd(c->device);
     slos_blk_destroy(c);
+    slos_mu_destroy(c);
     cudaFree(c->d_bt);
     cudaFree(c->d_dt);
     cudaFree(c->d_status);

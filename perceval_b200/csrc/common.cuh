@@ -22,6 +22,7 @@ struct fock_ctx {
     double *d_scratch; // small scratch (sum accumulators)
     uint64_t launches;
     void *blk_state;   // owned by slos_blk.cu (column tables, cached layer plans)
+    void *mu_state;    // owned by slos_mu.cu (cached tail occupation tables)
 };
 
 void fock_set_error(const char *fmt, ...);

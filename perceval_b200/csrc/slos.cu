@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "slos_tile.cuh"
 
 #define SLOS_BLOCK 256
 
@@ -187,7 +188,6 @@ __global__ void __launch_bounds__(SLOS_BLOCK) slos_epilogue_kernel(int m, int n,
 // are un-ranked cooperatively, one prefix per thread, into shared memory and read back as broadcasts.
 // Classes with S < 256 pack G = 256 / S prefixes per sweep step so the lanes stay busy.
 // ================================================================================================================
-#define TILE_BLOCK 256
 
 __device__ __forceinline__ double c_factorial(int n) {   // exact for n <= 22, correctly rounded products beyond
     double f = 1.0;
@@ -195,36 +195,6 @@ __device__ __forceinline__ double c_factorial(int n) {   // exact for n <= 22, c
     return f;
 }
 #define TILE_DB 128   // descriptors per batch
-
-struct TileClass {
-    int w, u;
-    uint32_t S, G, nchunks, pad;
-    uint64_t rho_lo, np;      // prefix ranks [rho_lo, rho_lo + np) of FS(p, w) intersect the child range
-    uint64_t item_begin;      // first work item (CTA index) of this class
-    uint64_t per_item;        // prefixes per work item
-};
-
-struct TileArgs {
-    int m, k, mk, p, ncls, maxnz;
-    const uint64_t *bt, *dt;
-    const double2 *U;
-    const double2 *parent;
-    uint64_t pbegin, pend;
-    double2 *child;
-    double *probs;
-    double *sum;
-    double inv_in_fact;
-    uint64_t cbegin, cend;
-    int *status;
-    int nslots;                // pipelined kernel: shared-memory slots per thread and buffer
-    TileClass cls[FOCK_TMAX];
-};
-
-struct __align__(16) TileDesc {
-    uint64_t cbase, tbase;
-    double pfact;
-    int nz, pad;
-};
 
 #define TILE_VP 4   // prefix edges whose loads are issued together with the tail loads
 #define TILE_TB 8   // tail parents loaded per batch
@@ -279,7 +249,37 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
     double tfact = 1.0;
 #pragma unroll
     for (int c = 0; c < D; ++c) toff[c] = 0;
-    if (active) {
+    const uint64_t *__restrict__ tuples = a.tup[ci];
+    if (active && tuples != nullptr) {
+        // fast set-up: the occupation tuple of tail rank t comes from the table cached per (D, u) (slos_mu.cu), so T_i / E_i
+        // are running sums with independent table look-ups, and the (offset, mode) pairs of the occupied modes are
+        // compacted through a private shared-memory column instead of D*D predicated moves.  The set-up is not
+        // amortised for the classes with few prefixes (w <= 3 holds 40 % of the children at 12 photons / 24 modes): the
+        // searching un-rank below cost 27 % of the kernel there (profiles/README.md).
+        uint2 *s_col = (uint2 *)(e_pb + TILE_DB * maxnz) + tid;   // entry c of this thread at s_col[c * TILE_BLOCK]
+        const uint64_t tup = __ldg(tuples + t);
+        uint32_t E = 0;
+        int T = u;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const int si = (int)((tup >> (4 * (i & 15))) & 15u);
+            T -= si;
+            if (si > 0) {
+                s_col[cnt * TILE_BLOCK] = make_uint2(t - E, (uint32_t)i);
+                ++cnt;
+                tfact *= s_fact[si];
+            }
+            if (i < D - 1 && T > 0) E += (uint32_t)s_dt[(D - 1 - i) * FOCK_TMAX + T];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            if (c < cnt) {
+                const uint2 v = s_col[c * TILE_BLOCK];
+                toff[c] = v.x;
+                tmode[c / 6] |= v.y << (5 * (c % 6));
+            }
+        }
+    } else if (active) {
         uint64_t rem = t;
         uint32_t E = 0;
         int Tprev = u;
@@ -805,6 +805,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_pipe_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------- host side
+bool slos_mu_supports(int D, int k);
+int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);                   // slos_mu.cu
+int slos_mu_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_blk_tail_modes(int m);                 // slos_blk.cu
 int slos_blk_u_limit(fock_ctx *c, int D, int k);
 int slos_layer_blocks(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, double *d_child,
@@ -908,7 +911,9 @@ static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
 
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
-                            uint64_t ce, cudaStream_t st, int u_from = 0) {
+                            uint64_t ce, cudaStream_t st, int u_from = 0, int gfilter = 0) {
+    // gfilter: 0 = every class, 1 = only classes whose tail block fills a CTA (S >= 256; v4 kernel, slos_mu.cu),
+    //          2 = only the small classes (S < 256; v2 kernel)
     const int p = m - D;
     TileArgs a;
     memset(&a, 0, sizeof a);
@@ -933,6 +938,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         if (u < u_from) continue;   // classes below u_from are handled by the block-staged kernel (slos_blk.cu)
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
+        if ((gfilter == 1 && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
         uint64_t lo = 0, hi = np_total;
         if (!full) {
             // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
@@ -959,8 +965,18 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     FOCK_REQUIRE(items < (1ull << 31), FOCK_ERR_LIMIT, "slos: too many work items");
     size_t smem = (size_t)2 * m * FOCK_TMAX * 8 + (size_t)m * 16 + 34 * 8 + (size_t)TILE_DB * sizeof(TileDesc) +
                   (size_t)TILE_DB * a.maxnz * 24 + 16;
+    {
+        static int fast_setup = -1;
+        if (fast_setup < 0) fast_setup = slos_env_int("FOCK_TILE_FAST_SETUP", 1);
+        if (fast_setup && D <= 16 && k <= 15) {   // cached occupation tuples (4 bits / tail mode): see slos_mu.cu
+            for (int i = 0; i < ncls; ++i)
+                if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
+            smem += (size_t)D * TILE_BLOCK * 8;
+        }
+    }
     const bool check = !(pb == 0 && pe == fock_count(m, k - 1)) || !full;
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
+    if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
     // lean variant when the whole parent layer is resident (no parent-window checks needed)
     {
         static int use_lean = -1;
@@ -1044,6 +1060,16 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
             return FOCK_OK;
         }
         const int D = slos_tail_modes(m);
+        static int use_mu = -1;
+        if (use_mu < 0) {
+            const char *e = getenv("FOCK_SLOS_KERNEL");
+            use_mu = (e && !strcmp(e, "v4")) ? 1 : 0;
+        }
+        if (D > 0 && use_mu && parent_full && slos_mu_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
+            // v4 (slos_mu.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 1)) return rc;
+            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
+        }
         if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st);
     }
     SlosArgs a;

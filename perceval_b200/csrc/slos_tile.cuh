@@ -1,0 +1,37 @@
+// slos_tile.cuh -- work-plan structures shared by the SLOS tile kernels (slos.cu: v2 family, slos_mu.cu: v4).
+#pragma once
+#include "common.cuh"
+
+#define TILE_BLOCK 256
+
+struct TileClass {
+    int w, u;
+    uint32_t S, G, nchunks, pad;
+    uint64_t rho_lo, np;      // prefix ranks [rho_lo, rho_lo + np) of FS(p, w) intersect the child range
+    uint64_t item_begin;      // first work item (CTA index) of this class
+    uint64_t per_item;        // prefixes per work item
+};
+
+struct TileArgs {
+    int m, k, mk, p, ncls, maxnz;
+    const uint64_t *bt, *dt;
+    const double2 *U;
+    const double2 *parent;
+    uint64_t pbegin, pend;
+    double2 *child;
+    double *probs;
+    double *sum;
+    double inv_in_fact;
+    uint64_t cbegin, cend;
+    int *status;
+    int nslots;                // pipelined kernel: shared-memory slots per thread and buffer
+    TileClass cls[FOCK_TMAX];
+    const uint64_t *tup[FOCK_TMAX];   // v4 kernel: per class, the occupation tuple (4 bits / tail mode) of every tail rank
+};
+
+struct __align__(16) TileDesc {
+    uint64_t cbase, tbase;
+    double pfact;
+    int nz, pad;
+};
+
