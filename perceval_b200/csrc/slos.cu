@@ -199,7 +199,8 @@ __device__ __forceinline__ double c_factorial(int n) {   // exact for n <= 22, c
 #define TILE_VP 4   // prefix edges whose loads are issued together with the tail loads
 #define TILE_TB 8   // tail parents loaded per batch
 
-template <int D, int MODE, bool CHECK>
+// CHECK: 0 = whole layers, 1 = child range only (sharded child, resident parent layer), 2 = child range + parent window
+template <int D, int MODE, int CHECK>
 __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_constant__ TileArgs a) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     const int m = a.m, p = a.p, maxnz = a.maxnz;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
         for (int i = (int)g; i < nb; i += (int)G) {
             const TileDesc td = s_desc[i];
             const uint64_t r = td.cbase + t;
-            if (CHECK && (r < a.cbegin || r >= a.cend)) continue;
+            if (CHECK >= 1 && (r < a.cbegin || r >= a.cend)) continue;
             const uint64_t *pb = e_pb + i * maxnz;
             const double2 *pu = e_u + i * maxnz;
             const int nz = td.nz;
@@ -368,14 +369,14 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
 #pragma unroll
             for (int e = 0; e < TILE_VP; ++e) {
                 if (e < nz) {
-                    if (CHECK && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; pv[e] = make_double2(0.0, 0.0); }
+                    if (CHECK == 2 && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; pv[e] = make_double2(0.0, 0.0); }
                     else pv[e] = parent_t[pb[e]];
                 }
             }
 #pragma unroll
             for (int c = 0; c < TILE_TB && c < D; ++c) {
                 if (c < wcnt) {
-                    if (CHECK && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c] = make_double2(0.0, 0.0); }
+                    if (CHECK == 2 && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c] = make_double2(0.0, 0.0); }
                     else tv[c] = tbp[toff[c]];
                 }
             }
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
             for (int e = 0; e < TILE_VP; ++e)
                 if (e < nz) acc = cfma(pu[e], pv[e], acc);
             for (int e = TILE_VP; e < nz; ++e) {
-                if (CHECK && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; continue; }
+                if (CHECK == 2 && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; continue; }
                 acc = cfma(pu[e], parent_t[pb[e]], acc);
             }
 #pragma unroll
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
 #pragma unroll
                     for (int c = c0; c < c0 + TILE_TB && c < D; ++c) {
                         if (c < wcnt) {
-                            if (CHECK && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c - c0] = make_double2(0.0, 0.0); }
+                            if (CHECK == 2 && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c - c0] = make_double2(0.0, 0.0); }
                             else tv[c - c0] = tbp[toff[c]];
                         }
                     }
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
             }
         }
     }
-    if (CHECK && oob && a.status) atomicExch(a.status, 1);
+    if (CHECK == 2 && oob && a.status) atomicExch(a.status, 1);
     if ((MODE & 2) && a.sum) {
         local_sum = warp_sum(local_sum);
         if ((tid & 31) == 0) s_red[tid >> 5] = local_sum;
@@ -895,15 +896,22 @@ static int launch_pipe(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
 }
 
 template <int D>
-static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, bool check, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, int check, unsigned grid, size_t smem, cudaStream_t st) {
 #define TILE_LAUNCH(MODE, CHK)                                                                                              \
     do {                                                                                                                  \
         FOCK_CUDA(cudaFuncSetAttribute(slos_tile_kernel<D, MODE, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         slos_tile_kernel<D, MODE, CHK><<<grid, TILE_BLOCK, smem, st>>>(a);                                                \
     } while (0)
-    if (want_probs && want_child) { if (check) TILE_LAUNCH(3, true); else TILE_LAUNCH(3, false); }
-    else if (want_probs) { if (check) TILE_LAUNCH(2, true); else TILE_LAUNCH(2, false); }
-    else { if (check) TILE_LAUNCH(1, true); else TILE_LAUNCH(1, false); }
+#define TILE_LAUNCH_CHK(MODE)                                                                                             \
+    do {                                                                                                                  \
+        if (check == 2) TILE_LAUNCH(MODE, 2);                                                                             \
+        else if (check == 1) TILE_LAUNCH(MODE, 1);                                                                        \
+        else TILE_LAUNCH(MODE, 0);                                                                                        \
+    } while (0)
+    if (want_probs && want_child) TILE_LAUNCH_CHK(3);
+    else if (want_probs) TILE_LAUNCH_CHK(2);
+    else TILE_LAUNCH_CHK(1);
+#undef TILE_LAUNCH_CHK
 #undef TILE_LAUNCH
     c->launches++;
     return fock_check_cuda(cudaGetLastError(), "slos_tile_kernel");
@@ -974,7 +982,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
             smem += (size_t)D * TILE_BLOCK * 8;
         }
     }
-    const bool check = !(pb == 0 && pe == fock_count(m, k - 1)) || !full;
+    const int check = !(pb == 0 && pe == fock_count(m, k - 1)) ? 2 : (full ? 0 : 1);
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
     if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
     // lean variant when the whole parent layer is resident (no parent-window checks needed)

@@ -270,6 +270,31 @@ def test_slos_tile_kernel_sharded_ranges(eng, oracle, m, k):
         eng.check_status()
 
 
+def test_slos_probs_to_host_pipelined():
+    """FockEngine.slos_probs_to_host: last layer in pieces, device->host copies on a side stream (bench.py's e2e path)."""
+    eng = _engine()
+    m, st = 16, (2, 1, 1, 1, 1, 1) + (0,) * 10
+    u = oracle.random_unitary(m, seed=11)
+    U = eng.unitary(u)
+    ref = oracle.slos_probs(u, st)
+    N = ref.shape[0]
+    host = torch.empty(N, dtype=torch.float64).pin_memory()
+    for pieces in (1, 3, 7):
+        host.zero_()
+        psum = eng.slos_probs_to_host(U, st, host, pieces=pieces)
+        torch.cuda.synchronize()
+        assert rel_err(host.numpy(), ref) < REL
+        assert abs(float(psum.item()) - 1.0) < 1e-12
+    # a rank range only (what one rank of a sharded run copies out)
+    b, e = N // 3 + 5, 2 * N // 3 + 1
+    part = torch.empty(e - b, dtype=torch.float64).pin_memory()
+    psum = eng.slos_probs_to_host(U, st, part, pieces=4, child_begin=b, child_end=e)
+    torch.cuda.synchronize()
+    assert rel_err(part.numpy(), ref[b:e]) < REL
+    assert abs(float(psum.item()) - ref[b:e].sum()) < 1e-12
+    eng.check_status()
+
+
 # ---------------------------------------------------------------- experimental SLOS kernels (selected by environment variable)
 
 _VARIANT_SCRIPT = r"""
