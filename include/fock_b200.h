@@ -53,6 +53,17 @@ int fock_unrank(fock_ctx *ctx, int m, int n, const uint64_t *d_ranks, uint64_t c
 /* states [begin,end) of FSArray(m,n) in order, written as (end-begin) x m uint8 */
 int fock_enumerate(fock_ctx *ctx, int m, int n, uint64_t begin, uint64_t end, uint8_t *d_states, void *stream);
 
+/* ---- FSMask  (replaces xq.FSMask(m, n, masks[, at_least_modes]).match(state[, allow_missing]),
+ *      perceval/backends/_abstract_backends.py:130-137 ; perceval/simulators/simulator.py:650-662 ;
+ *      tests/utils/test_mask.py:32-45) -------------------------------------------------------------------- */
+/* h_conds: nmask x m int8, -1 = any count, v >= 0 = exactly v photons (">= v" on modes whose bit is set in
+ * at_least_bits); a state matches if it matches any mask.  allow_missing != 0 is the partial match of intermediate
+ * layers.  d_flags[i] = 1 iff state #(begin+i) of FSArray(m,n) matches.  Synchronises `stream`. */
+int fock_mask_match(fock_ctx *ctx, int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
+                    uint64_t begin, uint64_t end, uint8_t *d_flags, void *stream);
+int fock_mask_match_host(int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
+                         const uint8_t *h_states, uint64_t cnt, uint8_t *h_flags);
+
 /* ---- SLOS  (replaces xq.FSMap(fsa_k, fsa_km1, True).compute_slos_layer(u, m, mk, coefs, parent_coefs),
  *      perceval/backends/_slos.py:99 ; python twin :91-97) ------------------------------------------------- */
 /* One layer: child[s] = sum_{j: s_j>0} U[j,mk] * parent[s - e_j] for child ranks [child_begin, child_end) of

@@ -27,6 +27,8 @@ SYMBOLS = [
     ("fock_rank", _i32, [_vp, _i32, _i32, _vp, _u64, _vp, _vp]),
     ("fock_unrank", _i32, [_vp, _i32, _i32, _vp, _u64, _vp, _vp]),
     ("fock_enumerate", _i32, [_vp, _i32, _i32, _u64, _u64, _vp, _vp]),
+    ("fock_mask_match", _i32, [_vp, _i32, _i32, _vp, _i32, _u64, _i32, _u64, _u64, _vp, _vp]),
+    ("fock_mask_match_host", _i32, [_i32, _i32, _vp, _i32, _u64, _i32, _vp, _u64, _vp]),
     ("slos_layer", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _u64, _u64, _vp, _u64, _u64, _vp]),
     ("slos_layer_probs", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _u64, _u64, _vp, _vp, _vp, _dbl, _u64, _u64, _vp]),
     ("slos_probs_epilogue", _i32, [_vp, _i32, _i32, _vp, _dbl, _vp, _vp, _u64, _u64, _vp]),

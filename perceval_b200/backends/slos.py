@@ -137,12 +137,30 @@ class SLOSB200Backend(AStrongSimulationBackend):
         return self._probs[st]
 
     def _mask_indices(self, st):
-        """Ranks (into the full FSArray) of the states the current mask keeps, or None without mask."""
+        """Device int64 ranks (into the full FSArray) of the states the current mask keeps, or None without mask.
+        The FSMask predicate runs on the device over the whole rank space (C ABI fock_mask_match)."""
         if self._mask is None:
             return None
-        states = self._get_iterator(st)
-        arr = np.array([[int(x) for x in s] for s in states], dtype=np.uint8).reshape(-1, st.m)
-        return fsarray.rank_states(st.m, st.n, arr).astype(np.int64)
+        key = (st.m, st.n)
+        if key not in self._mask_ranks:
+            self._mask_ranks[key] = self._eng().mask_ranks(st.m, st.n, self._mask)
+        return self._mask_ranks[key]
+
+    def clear_iterator_cache(self):
+        super().clear_iterator_cache()
+        self._mask_ranks = {}
+
+    def _get_iterator(self, input_state):
+        """Same contract as _abstract_backends.py:148-158 (tuple of output states, cached per photon count).  With a mask
+        only the kept ranks are un-ranked, on the device, instead of walking the whole FSArray in Python."""
+        n = input_state.n
+        if self._mask is None or self._input_state is None or n != self._input_state.n:
+            return super()._get_iterator(input_state)
+        if n not in self._cache_iterator:
+            ranks = self._mask_indices(input_state)
+            occ = self._eng().unrank(input_state.m, n, ranks).cpu().numpy()
+            self._cache_iterator[n] = tuple(FockState([int(x) for x in row]) for row in occ)
+        return self._cache_iterator[n]
 
     # ------------------------------------------------------------------ reference API (_slos.py:187-223)
     def prob_amplitude(self, output_state) -> complex:
@@ -165,7 +183,7 @@ class SLOSB200Backend(AStrongSimulationBackend):
         probs = self._get_probs(st)
         idx = self._mask_indices(st)
         if idx is not None:
-            probs = probs[torch.from_numpy(idx).to(probs.device)]
+            probs = probs[idx]
         return probs
 
     def all_amplitudes_tensor(self, input_state=None) -> torch.Tensor:
@@ -175,7 +193,7 @@ class SLOSB200Backend(AStrongSimulationBackend):
         amps = self._eng().slos_amplitudes_from_coefs(st.m, st.n, self._get_coefs(st), prodnfact(st))
         idx = self._mask_indices(st)
         if idx is not None:
-            amps = amps[torch.from_numpy(idx).to(amps.device)]
+            amps = amps[idx]
         return amps
 
     def coefs_tensor(self, input_state=None) -> torch.Tensor:
@@ -201,7 +219,7 @@ class SLOSB200Backend(AStrongSimulationBackend):
         idx = self._mask_indices(st)
         if idx is not None:
             allowed = torch.zeros_like(keep)
-            allowed[torch.from_numpy(idx).to(keep.device)] = True
+            allowed[idx] = True
             keep &= allowed
         ranks = torch.nonzero(keep).view(-1)
         return ranks, probs[ranks]

@@ -281,3 +281,82 @@ extern "C" int fock_enumerate(fock_ctx *c, int m, int n, uint64_t begin, uint64_
     FOCK_CUDA(cudaGetLastError());
     return FOCK_OK;
 }
+
+// ---- FSMask on the device (replaces xq.FSMask(m, n, masks[, at_least_modes]).match(state) over a whole FSArray,
+// reference perceval/backends/_abstract_backends.py:130-137, tests/utils/test_mask.py:32-45): flags[i] = 1 iff state
+// #(begin+i) of FSArray(m, n) matches ANY mask.  conds holds nmask*m int8: -1 accepts anything, v >= 0 fixes the count
+// (">= v" on the modes whose bit is set in at_least_bits).  allow_missing is the partial match used on intermediate
+// layers: a mode passes if its count can still grow into the condition.
+#define FOCK_MASK_MAXCOND 2048
+__constant__ signed char c_mask_cond[FOCK_MASK_MAXCOND];
+
+__host__ __device__ inline bool mask_match_one(const uint8_t *st, int m, const signed char *cond, int nmask, uint64_t at_least_bits, int allow_missing) {
+    for (int k = 0; k < nmask; ++k) {
+        const signed char *cd = cond + k * m;
+        bool ok = true;
+        for (int i = 0; i < m && ok; ++i) {
+            const int c = cd[i];
+            if (c < 0) continue;
+            const int v = st[i];
+            const bool ge = i < 64 && ((at_least_bits >> i) & 1ull);
+            if (allow_missing) ok = ge || v <= c;
+            else ok = ge ? (v >= c) : (v == c);
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) mask_match_kernel(int m, int n, const uint64_t *__restrict__ bt, int nmask, uint64_t at_least_bits,
+                                                         int allow_missing, uint64_t first, uint64_t cnt, uint8_t *__restrict__ flags) {
+    __shared__ uint64_t s_bt[FOCK_QMAX * FOCK_TMAX];
+    for (int i = threadIdx.x; i < m * FOCK_TMAX; i += blockDim.x) s_bt[i] = bt[i];
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t rem = first + i;
+        uint8_t st[FOCK_QMAX];
+        int Tprev = n;
+        for (int j = 0; j < m - 1; ++j) {
+            const uint64_t *row = s_bt + (m - 1 - j) * FOCK_TMAX;
+            int T = Tprev;
+            while (row[T] > rem) --T;
+            rem -= row[T];
+            st[j] = (uint8_t)(Tprev - T);
+            Tprev = T;
+        }
+        st[m - 1] = (uint8_t)Tprev;
+        flags[i] = mask_match_one(st, m, c_mask_cond, nmask, at_least_bits, allow_missing) ? 1 : 0;
+    }
+}
+
+static int mask_check(const char *who, int m, int n, const int8_t *h_conds, int nmask) {
+    if (int rc = check_mn(who, m, n)) return rc;
+    FOCK_REQUIRE(h_conds != nullptr && nmask >= 1, FOCK_ERR_ARG, "%s: no mask conditions", who);
+    FOCK_REQUIRE((size_t)nmask * m <= FOCK_MASK_MAXCOND, FOCK_ERR_LIMIT, "%s: more than %d mask conditions", who, FOCK_MASK_MAXCOND);
+    return FOCK_OK;
+}
+
+extern "C" int fock_mask_match(fock_ctx *c, int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
+                               uint64_t begin, uint64_t end, uint8_t *d_flags, void *stream) {
+    FOCK_REQUIRE(c != nullptr && d_flags != nullptr, FOCK_ERR_ARG, "fock_mask_match: NULL argument");
+    if (int rc = mask_check("fock_mask_match", m, n, h_conds, nmask)) return rc;
+    FOCK_REQUIRE(begin <= end && end <= fock_count(m, n), FOCK_ERR_ARG, "fock_mask_match: bad range");
+    if (begin == end) return FOCK_OK;
+    ScopedDevice sd(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    FOCK_CUDA(cudaMemcpyToSymbolAsync(c_mask_cond, h_conds, (size_t)nmask * m, 0, cudaMemcpyHostToDevice, st));
+    mask_match_kernel<<<grid_for(c, end - begin, 256), 256, 0, st>>>(m, n, c->d_bt, nmask, at_least_bits, allow_missing, begin, end - begin, d_flags);
+    c->launches++;
+    FOCK_CUDA(cudaGetLastError());
+    FOCK_CUDA(cudaStreamSynchronize(st));   // h_conds may be pageable host memory: it must stay valid until the copy ran
+    return FOCK_OK;
+}
+
+extern "C" int fock_mask_match_host(int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
+                                    const uint8_t *h_states, uint64_t cnt, uint8_t *h_flags) {
+    FOCK_REQUIRE(h_states != nullptr && h_flags != nullptr, FOCK_ERR_ARG, "fock_mask_match_host: NULL argument");
+    if (int rc = mask_check("fock_mask_match_host", m, n, h_conds, nmask)) return rc;
+    for (uint64_t i = 0; i < cnt; ++i)
+        h_flags[i] = mask_match_one(h_states + i * (uint64_t)m, m, (const signed char *)h_conds, nmask, at_least_bits, allow_missing) ? 1 : 0;
+    return FOCK_OK;
+}

@@ -102,6 +102,20 @@ class FockEngine:
         check(self.lib.fock_enumerate(self.ctx, m, n, begin, end, out.data_ptr(), self._stream()), "fock_enumerate")
         return out
 
+    # ------------------------------------------------------------------ FSMask
+    def mask_flags(self, m: int, n: int, mask, begin: int = 0, end: int | None = None, allow_missing: bool = False) -> torch.Tensor:
+        """uint8 device tensor: 1 where state #(begin+i) of FSArray(m, n) matches ``mask`` (a masks.FockMask)."""
+        end = self.count(m, n) if end is None else end
+        conds = mask.conds_array()
+        flags = torch.empty(end - begin, dtype=torch.uint8, device=self.device)
+        check(self.lib.fock_mask_match(self.ctx, m, n, conds.ctypes.data_as(C.c_void_p), conds.shape[0], mask.at_least_bits(),
+                                       1 if allow_missing else 0, begin, end, flags.data_ptr(), self._stream()), "fock_mask_match")
+        return flags
+
+    def mask_ranks(self, m: int, n: int, mask) -> torch.Tensor:
+        """Ranks (int64, ascending = FSArray order) of the states of FSArray(m, n) the mask keeps."""
+        return torch.nonzero(self.mask_flags(m, n, mask)).view(-1)
+
     # ------------------------------------------------------------------ SLOS
     def slos_order(self, state) -> list:
         s = _state_u8(state)

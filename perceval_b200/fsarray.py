@@ -29,6 +29,11 @@ def unrank(m: int, n: int, ranks) -> np.ndarray:
     return out
 
 
+def enumerate_states(m: int, n: int) -> np.ndarray:
+    """All states of FSArray(m, n) in order as a (count, m) uint8 array."""
+    return unrank(m, n, np.arange(count(m, n), dtype=np.uint64))
+
+
 def iterate_states(m: int, n: int, chunk: int = 1 << 16):
     """Occupation tuples of FSArray(m, n) in order (descending lexicographic)."""
     total = count(m, n)

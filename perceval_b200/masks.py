@@ -44,6 +44,17 @@ class FockMask:
                 return True
         return False
 
+    def conds_array(self) -> np.ndarray:
+        """(nmask, m) int8 for the C ABI (fock_mask_match): -1 accepts anything, v >= 0 fixes the photon count."""
+        return np.ascontiguousarray(np.array([[-1 if c is None else int(c) for c in cond] for cond in self.conds], dtype=np.int8))
+
+    def at_least_bits(self) -> int:
+        bits = 0
+        for i in self.at_least:
+            assert 0 <= i < 64
+            bits |= 1 << int(i)
+        return bits
+
     def match_array(self, states: np.ndarray) -> np.ndarray:
         """Vectorised exact match over a (count, m) uint8 array -> bool mask."""
         keep = np.zeros(states.shape[0], dtype=bool)

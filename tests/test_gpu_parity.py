@@ -270,9 +270,8 @@ def test_slos_tile_kernel_sharded_ranges(eng, oracle, m, k):
         eng.check_status()
 
 
-def test_slos_probs_to_host_pipelined():
+def test_slos_probs_to_host_pipelined(eng, oracle):
     """FockEngine.slos_probs_to_host: last layer in pieces, device->host copies on a side stream (bench.py's e2e path)."""
-    eng = _engine()
     m, st = 16, (2, 1, 1, 1, 1, 1) + (0,) * 10
     u = oracle.random_unitary(m, seed=11)
     U = eng.unitary(u)
