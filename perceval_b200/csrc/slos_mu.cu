@@ -59,7 +59,7 @@ __device__ __forceinline__ void mu_sweep(const TileArgs &a, const MuShared &sh, 
                                          const uint32_t t, const int u, const int w, const uint64_t rho_a, const uint64_t rho_b,
                                          const double tfact, const bool active, double &local_sum) {
     constexpr int FIRST = W < 8 ? W : 8;
-    constexpr int URES = W < 8 ? W : 8;   // unitary entries of the first URES slots stay in registers for the whole sweep
+    constexpr int URES = 0;   // unitary entries of the first URES slots stay in registers for the whole sweep
     double2 ures[URES > 0 ? URES : 1];
 #pragma unroll
     for (int c = 0; c < URES; ++c) ures[c] = mu_lds16((c & 1) ? (uadr[c / 2] >> 16) : (uadr[c / 2] & 0xFFFFu));
@@ -133,7 +133,7 @@ __device__ __forceinline__ void mu_sweep(const TileArgs &a, const MuShared &sh, 
             for (int e = 4; e < nz; ++e) acc = cfma(pu[e], mu_ld_row((const char *)ep[e], t16), acc);
 #pragma unroll
             for (int c = 0; c < FIRST; ++c) {
-                const double2 uc = c < URES ? ures[c] : mu_lds16((c & 1) ? (uadr[c / 2] >> 16) : (uadr[c / 2] & 0xFFFFu));
+                const double2 uc = c < URES ? ures[c] : ((a.nslots & 4) ? make_double2(0.5, 0.25) : mu_lds16((c & 1) ? (uadr[c / 2] >> 16) : (uadr[c / 2] & 0xFFFFu)));
                 if (c & 1) acb = cfma(uc, tv[c], acb);
                 else acc = cfma(uc, tv[c], acc);
             }
