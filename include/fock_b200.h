@@ -80,6 +80,16 @@ int slos_layer_probs(fock_ctx *ctx, int m, int k, const double *d_U, int mk, con
                      uint64_t parent_begin, uint64_t parent_end, double *d_child, double *d_probs, double *d_sum,
                      double in_prodnfact, uint64_t child_begin, uint64_t child_end, void *stream);
 
+/* Same two calls with a SEGMENTED resident parent: h_parent_seg = {b0, e0, b1, e1}, e0 <= b1, ranks [b0,e0) then
+ * [b1,e1) stored packed at d_parent (b1 == e1: one segment).  The parents a contiguous child range needs through one
+ * mode are one contiguous range (perceval/backends/_slos.py:91-97 read as a gather), their union over the modes one or
+ * two ranges -- the recompute-window partition of perceval_b200/dist.py keeps only those resident. */
+int slos_layer_seg(fock_ctx *ctx, int m, int k, const double *d_U, int mk, const double *d_parent, const uint64_t *h_parent_seg,
+                   double *d_child, uint64_t child_begin, uint64_t child_end, void *stream);
+int slos_layer_probs_seg(fock_ctx *ctx, int m, int k, const double *d_U, int mk, const double *d_parent,
+                         const uint64_t *h_parent_seg, double *d_child, double *d_probs, double *d_sum, double in_prodnfact,
+                         uint64_t child_begin, uint64_t child_end, void *stream);
+
 /* Stand-alone epilogues on an existing coefficient range [begin,end) of FSArray(m,n). */
 int slos_probs_epilogue(fock_ctx *ctx, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,
                         double *d_sum, uint64_t begin, uint64_t end, void *stream);

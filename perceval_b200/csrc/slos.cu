@@ -28,8 +28,8 @@ struct SlosArgs {
     int m, k, mk;
     const uint64_t *bt, *dt;
     const double2 *U;        // m*m row-major
-    const double2 *parent;   // parent ranks [pbegin, pend)
-    uint64_t pbegin, pend;
+    const double2 *parent;   // parent ranks [pbegin, pend) minus the hole [gap_b, gap_e), stored packed
+    uint64_t pbegin, pend, gap_b, gap_e;
     double2 *child;          // child ranks [cbegin, cend) (may be null when probs only)
     double *probs;           // may be null
     double *sum;             // may be null
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(SLOS_BLOCK) slos_layer_gather_kernel(const Slo
             const int si = Tprev - T;
             if (si > 0) {
                 const uint64_t pr = r - E;
-                if (pr < a.pbegin || pr >= a.pend) oob = true;
-                else acc = cfma(s_u[i], parent[pr], acc);
+                if (pr < a.pbegin || pr >= a.pend || (pr >= a.gap_b && pr < a.gap_e)) oob = true;
+                else acc = cfma(s_u[i], parent[pr >= a.gap_e ? pr - (a.gap_e - a.gap_b) : pr], acc);
                 if (MODE & 2) fact *= s_fact[si];
             }
             if (T == 0) break;  // every remaining mode is empty
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(SLOS_BLOCK) slos_layer_gather_kernel(const Slo
         }
         if (i == m - 1 && Tprev > 0) {  // last mode holds the remaining photons
             const uint64_t pr = r - E;
-            if (pr < a.pbegin || pr >= a.pend) oob = true;
-            else acc = cfma(s_u[m - 1], parent[pr], acc);
+            if (pr < a.pbegin || pr >= a.pend || (pr >= a.gap_b && pr < a.gap_e)) oob = true;
+            else acc = cfma(s_u[m - 1], parent[pr >= a.gap_e ? pr - (a.gap_e - a.gap_b) : pr], acc);
             if (MODE & 2) fact *= s_fact[Tprev];
         }
         if (MODE & 1) a.child[r - a.cbegin] = acc;
@@ -195,6 +195,16 @@ __device__ __forceinline__ double c_factorial(int n) {   // exact for n <= 22, c
     return f;
 }
 #define TILE_DB 128   // descriptors per batch (256 -> one CTA per SM: 18.8 ms vs 15.0 ms for the last 12/24 layer)
+
+// window-checked parent load (CHECK == 2): false if rank r is not resident
+__device__ __forceinline__ bool tile_win_load(const TileArgs &a, const double2 *__restrict__ parent, uint64_t r, double2 &v) {
+    if (r < a.pbegin || r >= a.pend || (r >= a.gap_b && r < a.gap_e)) {
+        v = make_double2(0.0, 0.0);
+        return false;
+    }
+    v = parent[r >= a.gap_e ? r - (a.gap_e - a.gap_b) : r];
+    return true;
+}
 
 #define TILE_VP 4   // prefix edges whose loads are issued together with the tail loads
 #define TILE_TB 8   // tail parents loaded per batch
@@ -369,14 +379,14 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
 #pragma unroll
             for (int e = 0; e < TILE_VP; ++e) {
                 if (e < nz) {
-                    if (CHECK == 2 && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; pv[e] = make_double2(0.0, 0.0); }
+                    if (CHECK == 2) { if (!tile_win_load(a, parent, pb[e] + t, pv[e])) oob = true; }
                     else pv[e] = parent_t[pb[e]];
                 }
             }
 #pragma unroll
             for (int c = 0; c < TILE_TB && c < D; ++c) {
                 if (c < wcnt) {
-                    if (CHECK == 2 && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c] = make_double2(0.0, 0.0); }
+                    if (CHECK == 2) { if (!tile_win_load(a, parent, td.tbase + toff[c], tv[c]) && c < cnt) oob = true; }
                     else tv[c] = tbp[toff[c]];
                 }
             }
@@ -385,7 +395,12 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
             for (int e = 0; e < TILE_VP; ++e)
                 if (e < nz) acc = cfma(pu[e], pv[e], acc);
             for (int e = TILE_VP; e < nz; ++e) {
-                if (CHECK == 2 && (pb[e] + t < a.pbegin || pb[e] + t >= a.pend)) { oob = true; continue; }
+                if (CHECK == 2) {
+                    double2 v;
+                    if (!tile_win_load(a, parent, pb[e] + t, v)) { oob = true; continue; }
+                    acc = cfma(pu[e], v, acc);
+                    continue;
+                }
                 acc = cfma(pu[e], parent_t[pb[e]], acc);
             }
 #pragma unroll
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_c
 #pragma unroll
                     for (int c = c0; c < c0 + TILE_TB && c < D; ++c) {
                         if (c < wcnt) {
-                            if (CHECK == 2 && (td.tbase + toff[c] < a.pbegin || td.tbase + toff[c] >= a.pend)) { if (c < cnt) oob = true; tv[c - c0] = make_double2(0.0, 0.0); }
+                            if (CHECK == 2) { if (!tile_win_load(a, parent, td.tbase + toff[c], tv[c - c0]) && c < cnt) oob = true; }
                             else tv[c - c0] = tbp[toff[c]];
                         }
                     }
@@ -919,7 +934,8 @@ static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
 
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
-                            uint64_t ce, cudaStream_t st, int u_from = 0, int gfilter = 0) {
+                            uint64_t ce, cudaStream_t st, int u_from = 0, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
+                            uint64_t gap_e = UINT64_MAX) {
     // gfilter: 0 = every class, 1 = only classes whose tail block fills a CTA (S >= 256; v4 kernel, slos_mu.cu),
     //          2 = only the small classes (S < 256; v2 kernel)
     const int p = m - D;
@@ -932,6 +948,9 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     a.U = (const double2 *)d_U;
     a.parent = (const double2 *)d_parent;
     a.pbegin = pb; a.pend = pe;
+    const bool gapped = gap_b < gap_e && gap_b < pe;
+    a.gap_b = gapped ? gap_b : pe;
+    a.gap_e = gapped ? gap_e : pe;
     a.child = (double2 *)d_child;
     a.probs = d_probs;
     a.sum = d_sum;
@@ -982,7 +1001,8 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
             smem += (size_t)D * TILE_BLOCK * 8;
         }
     }
-    const int check = !(pb == 0 && pe == fock_count(m, k - 1)) ? 2 : (full ? 0 : 1);
+    const bool parent_whole = pb == 0 && pe == fock_count(m, k - 1) && !gapped;
+    const int check = !parent_whole ? 2 : (full ? 0 : 1);
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
     if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
     // lean variant when the whole parent layer is resident (no parent-window checks needed)
@@ -990,7 +1010,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         static int use_lean = -1;
         if (use_lean < 0) use_lean = slos_env_int("FOCK_TILE_LEAN", 0);   // measured 18.6 ms vs 16.0 ms (v2) for the last 12/24 layer
         const size_t lsmem = (size_t)m * 16 + (size_t)LEAN_DB * sizeof(LeanDesc) + (size_t)LEAN_DB * a.maxnz * 24 + 16;
-        if (use_lean && pb == 0 && pe == fock_count(m, k - 1) && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
+        if (use_lean && parent_whole && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
             switch (D) {
                 case 4: return launch_lean<4>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
                 case 6: return launch_lean<6>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
@@ -1014,7 +1034,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
                              (size_t)2 * nslots * TILE_BLOCK * 16;
         static int use_pipe = -1;
         if (use_pipe < 0) use_pipe = slos_env_int("FOCK_TILE_PIPE", 0);   // measured slower than the register-staged kernels
-        if (use_pipe && pb == 0 && pe == fock_count(m, k - 1) && psmem <= 113 * 1024 && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
+        if (use_pipe && parent_whole && psmem <= 113 * 1024 && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
             switch (D) {
                 case 4: return launch_pipe<4>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
                 case 6: return launch_pipe<6>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
@@ -1038,7 +1058,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
 
 static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                            uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
-                           uint64_t ce, void *stream, const char *who) {
+                           uint64_t ce, void *stream, const char *who, uint64_t gap_b = UINT64_MAX, uint64_t gap_e = UINT64_MAX) {
     if (int rc = slos_check(who, c, m, k)) return rc;
     FOCK_REQUIRE(k >= 1, FOCK_ERR_ARG, "%s: child layer must hold >= 1 photon", who);
     FOCK_REQUIRE(mk >= 0 && mk < m, FOCK_ERR_ARG, "%s: input mode %d outside [0,%d)", who, mk, m);
@@ -1058,7 +1078,8 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     }
     if (force != 1 && (ce - cb) >= 32768) {
         const int Db = slos_blk_tail_modes(m);
-        const bool parent_full = (pb == 0 && pe == fock_count(m, k - 1));
+        const bool gapped = gap_b < gap_e && gap_b < pe;
+        const bool parent_full = (pb == 0 && pe == fock_count(m, k - 1)) && !gapped;
         if (force == 0 && Db > 0 && parent_full && ((uintptr_t)d_parent & 15) == 0) {
             const int u_lim = slos_blk_u_limit(c, Db, k);
             FOCK_REQUIRE(u_lim > 0, FOCK_ERR_CUDA, "slos: could not build the tail tables");
@@ -1078,7 +1099,7 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
             if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 1)) return rc;
             return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
         }
-        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st);
+        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 0, gap_b, gap_e);
     }
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
@@ -1086,6 +1107,8 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     a.U = (const double2 *)d_U;
     a.parent = (const double2 *)d_parent;
     a.pbegin = pb; a.pend = pe;
+    a.gap_b = (gap_b < gap_e && gap_b < pe) ? gap_b : pe;
+    a.gap_e = (gap_b < gap_e && gap_b < pe) ? gap_e : pe;
     a.child = (double2 *)d_child;
     a.probs = d_probs;
     a.sum = d_sum;
@@ -1114,6 +1137,39 @@ extern "C" int slos_layer_probs(fock_ctx *c, int m, int k, const double *d_U, in
     FOCK_REQUIRE(in_prodnfact > 0, FOCK_ERR_ARG, "slos_layer_probs: in_prodnfact must be > 0");
     return slos_layer_impl(c, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, stream,
                            "slos_layer_probs");
+}
+
+// Segmented parent: the resident parent ranks are seg = {b0, e0, b1, e1} with e0 <= b1, stored packed (segment 0 then
+// segment 1; b1 == e1 means one segment).  Used by the recompute-window partition of a layer chain (dist.py): the parents
+// a contiguous child range needs through mode j are exactly one contiguous range, and their union over the modes is one
+// or two ranges.
+static int seg_check(const char *who, int m, int k, const uint64_t *seg) {
+    FOCK_REQUIRE(seg != nullptr, FOCK_ERR_ARG, "%s: parent_seg is NULL", who);
+    FOCK_REQUIRE(seg[0] <= seg[1] && seg[1] <= seg[2] && seg[2] <= seg[3] && seg[3] <= fock_count(m, k - 1), FOCK_ERR_ARG,
+                 "%s: parent segments must be ordered and inside the parent layer", who);
+    return FOCK_OK;
+}
+
+extern "C" int slos_layer_seg(fock_ctx *c, int m, int k, const double *d_U, int mk, const double *d_parent, const uint64_t *seg,
+                              double *d_child, uint64_t cb, uint64_t ce, void *stream) {
+    FOCK_REQUIRE(d_child != nullptr, FOCK_ERR_ARG, "slos_layer_seg: d_child is NULL");
+    FOCK_REQUIRE(k >= 1, FOCK_ERR_ARG, "slos_layer_seg: child layer must hold >= 1 photon");
+    if (int rc = seg_check("slos_layer_seg", m, k, seg)) return rc;
+    const bool two = seg[2] < seg[3];
+    return slos_layer_impl(c, m, k, d_U, mk, d_parent, seg[0], two ? seg[3] : seg[1], d_child, nullptr, nullptr, 1.0, cb, ce, stream,
+                           "slos_layer_seg", two ? seg[1] : UINT64_MAX, two ? seg[2] : UINT64_MAX);
+}
+
+extern "C" int slos_layer_probs_seg(fock_ctx *c, int m, int k, const double *d_U, int mk, const double *d_parent, const uint64_t *seg,
+                                    double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb, uint64_t ce,
+                                    void *stream) {
+    FOCK_REQUIRE(d_probs != nullptr, FOCK_ERR_ARG, "slos_layer_probs_seg: d_probs is NULL");
+    FOCK_REQUIRE(in_prodnfact > 0, FOCK_ERR_ARG, "slos_layer_probs_seg: in_prodnfact must be > 0");
+    FOCK_REQUIRE(k >= 1, FOCK_ERR_ARG, "slos_layer_probs_seg: child layer must hold >= 1 photon");
+    if (int rc = seg_check("slos_layer_probs_seg", m, k, seg)) return rc;
+    const bool two = seg[2] < seg[3];
+    return slos_layer_impl(c, m, k, d_U, mk, d_parent, seg[0], two ? seg[3] : seg[1], d_child, d_probs, d_sum, in_prodnfact, cb, ce,
+                           stream, "slos_layer_probs_seg", two ? seg[1] : UINT64_MAX, two ? seg[2] : UINT64_MAX);
 }
 
 extern "C" int slos_probs_epilogue(fock_ctx *c, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,

@@ -17,7 +17,8 @@ struct TileArgs {
     const uint64_t *bt, *dt;
     const double2 *U;
     const double2 *parent;
-    uint64_t pbegin, pend;
+    uint64_t pbegin, pend;     // resident parent ranks [pbegin, pend) ...
+    uint64_t gap_b, gap_e;     // ... except the hole [gap_b, gap_e): ranks >= gap_e are stored (gap_e - gap_b) elements earlier
     double2 *child;
     double *probs;
     double *sum;

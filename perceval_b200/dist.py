@@ -133,6 +133,63 @@ def engine_slos_probs_sharded(engine, U, in_state, group=None, exchange: str = "
     return slos_probs_sharded(m, occ, order, engine.count, layer_fn, last_fn, group, exchange)
 
 
+def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1):
+    """Sub-shards of a rank in the recompute-window partition: the rank's contiguous range of the output layer is cut in
+    ``sub`` pieces, each with its own chain plan (partition.plan_chain).  Returns [(begin, end, plan), ...]."""
+    from . import partition as P
+    N = P.count(m, n)
+    out = []
+    for i in range(sub):
+        b, e = shard_range(N, rank * sub + i, world * sub)
+        out.append((b, e, P.plan_chain(m, n, b, e)))
+    return out
+
+
+def windowed_peak_bytes(n: int, pieces) -> int:
+    """Device bytes the windowed chain needs at its worst moment: the two packed layer buffers of one sub-shard plus the
+    probabilities of the sub-shards already finished (8 B each) -- see engine_slos_probs_windowed."""
+    from . import partition as P
+    worst, done = 0, 0
+    for b, e, plan in pieces:
+        a = max([P.segments_len(plan[k]) for k in range(n - 1, -1, -2)] + [1])
+        bb = max([P.segments_len(plan[k]) for k in range(n - 2, -1, -2)] + [1])
+        worst = max(worst, done + 16 * (a + bb), done + 16 * a + 8 * (e - b))
+        done += 8 * (e - b)
+    return worst
+
+
+def engine_slos_probs_windowed(engine, U, in_state, group=None, sub: int | None = None, mem_fraction: float = 0.8):
+    """Recompute-window partition of the SLOS chain: NO exchange step.  Every rank owns a contiguous range of the output
+    layer and recomputes, layer by layer, exactly the parents that range needs (one or two rank ranges per layer,
+    partition.py), so no layer is ever replicated or gathered.  This is what lets 14 photons / 28 modes (layer 13 alone is
+    192 GB) run on 8 x 180 GB.  ``sub`` cuts the rank's range further to bound memory (None: smallest count whose peak
+    fits ``mem_fraction`` of the free device memory).  Returns (list of probability tensors, list of (begin, end),
+    total sum(p) tensor)."""
+    occ = [int(x) for x in in_state]
+    m, n = len(occ), sum(occ)
+    rank, world = _world(group)
+    if sub is None:
+        free, _total = torch.cuda.mem_get_info(engine.device)
+        sub = 1
+        while sub < 64 and windowed_peak_bytes(n, windowed_plan(m, n, rank, world, sub)) > mem_fraction * free:
+            sub += 1
+        if dist.is_available() and dist.is_initialized() and world > 1:   # same piece count everywhere keeps the ranges aligned
+            t = torch.tensor([sub], dtype=torch.int64, device=engine.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            sub = int(t.item())
+    pieces = windowed_plan(m, n, rank, world, sub)
+    psum = torch.zeros(1, dtype=torch.float64, device=engine.device)
+    outs, ranges = [], []
+    for b, e, plan in pieces:
+        probs, _, _ = engine.slos_probs_windowed(U, occ, b, e, psum=psum, plan=plan)
+        outs.append(probs)
+        ranges.append((b, e))
+        torch.cuda.empty_cache()   # the packed layer buffers of this piece are gone before the next piece allocates its own
+    if world > 1:
+        dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)
+    return outs, ranges, psum
+
+
 def permanents_sharded(perm_fn, mats: torch.Tensor, group=None):
     """Batch of permanents over ranks.  perm_fn(mats, gray_begin, gray_end) -> (B,) complex tensor (partial sums for a
     Gray sub-range, already scaled).  B >= world: split by matrix + all-gather; else split the Gray range + all-reduce."""

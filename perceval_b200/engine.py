@@ -148,6 +148,75 @@ class FockEngine:
                                         child_begin, child_end, self._stream()), "slos_layer_probs")
         return probs
 
+    def slos_layer_seg(self, m: int, k: int, U: torch.Tensor, mk: int, parent: torch.Tensor, parent_segs, child: torch.Tensor,
+                       child_begin: int, child_end: int) -> torch.Tensor:
+        """One layer from a SEGMENTED parent (C ABI slos_layer_seg): ``parent`` holds the ranks of ``parent_segs`` (one or
+        two (b, e) ranges, ascending) packed back to back; ``child`` receives ranks [child_begin, child_end)."""
+        from .partition import seg4, segments_len
+        assert parent.numel() >= segments_len(parent_segs) and child.numel() >= child_end - child_begin
+        seg = np.array(seg4(parent_segs), dtype=np.uint64)
+        check(self.lib.slos_layer_seg(self.ctx, m, k, U.data_ptr(), mk, parent.data_ptr(), seg.ctypes.data_as(C.c_void_p),
+                                      child.data_ptr(), child_begin, child_end, self._stream()), "slos_layer_seg")
+        return child
+
+    def slos_layer_probs_seg(self, m: int, k: int, U: torch.Tensor, mk: int, parent: torch.Tensor, parent_segs, in_prodnfact: float,
+                             probs: torch.Tensor, psum: torch.Tensor | None, child_begin: int, child_end: int) -> torch.Tensor:
+        from .partition import seg4, segments_len
+        assert parent.numel() >= segments_len(parent_segs) and probs.numel() >= child_end - child_begin
+        seg = np.array(seg4(parent_segs), dtype=np.uint64)
+        check(self.lib.slos_layer_probs_seg(self.ctx, m, k, U.data_ptr(), mk, parent.data_ptr(), seg.ctypes.data_as(C.c_void_p), None,
+                                            probs.data_ptr(), psum.data_ptr() if psum is not None else None, float(in_prodnfact),
+                                            child_begin, child_end, self._stream()), "slos_layer_probs_seg")
+        return probs
+
+    def slos_probs_windowed(self, U: torch.Tensor, in_state, child_begin: int, child_end: int, probs: torch.Tensor | None = None,
+                            psum: torch.Tensor | None = None, plan=None, buffers=None):
+        """Probabilities of the ranks [child_begin, child_end) of the output layer, keeping resident -- and computing --
+        only the parents of every layer that this range needs (partition.plan_chain): the recompute-window partition
+        of a multi-GPU run.  Returns (probs, psum, plan)."""
+        from . import partition as P
+        s = _state_u8(in_state)
+        m, n = len(s), int(s.sum())
+        assert n >= 1
+        order = self.slos_order(s)
+        if plan is None:
+            plan = P.plan_chain(m, n, child_begin, child_end)
+        if psum is None:
+            psum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        if child_end <= child_begin:
+            return (probs if probs is not None else torch.empty(0, dtype=torch.float64, device=self.device)), psum, plan
+        # two packed ping-pong buffers: layers n-1, n-3, ... in A; n-2, n-4, ... in B
+        need_a = max([P.segments_len(plan[k]) for k in range(n - 1, -1, -2)] + [1])
+        need_b = max([P.segments_len(plan[k]) for k in range(n - 2, -1, -2)] + [1])
+        if buffers is None:
+            buffers = (torch.empty(need_a, dtype=torch.complex128, device=self.device),
+                       torch.empty(need_b, dtype=torch.complex128, device=self.device))
+            own_buffers = True
+        else:
+            own_buffers = False
+        buf_a, buf_b = buffers
+        del buffers
+        assert buf_a.numel() >= need_a and buf_b.numel() >= need_b
+        cur = buf_a if ((n - 1) - 0) % 2 == 0 else buf_b   # layer k lives in A when (n-1-k) is even
+        cur[:1] = 1.0                                # layer 0 = the vacuum coefficient
+        parent, parent_segs = cur, [(0, 1)]
+        child_buf = None
+        for k in range(1, n):
+            child_buf = buf_a if ((n - 1) - k) % 2 == 0 else buf_b
+            off = 0
+            for b, e in plan[k]:
+                self.slos_layer_seg(m, k, U, order[k - 1], parent, parent_segs, child_buf[off:off + (e - b)], b, e)
+                off += e - b
+            parent, parent_segs = child_buf, plan[k]
+        if probs is None:
+            if own_buffers:   # layer n-1 sits in A: drop B before the probabilities are allocated (peak = max(A+B, A+probs))
+                del buf_b, child_buf, cur
+                torch.cuda.synchronize(self.device)
+                torch.cuda.empty_cache()
+            probs = torch.empty(child_end - child_begin, dtype=torch.float64, device=self.device)
+        self.slos_layer_probs_seg(m, n, U, order[n - 1], parent, parent_segs, prodnfact(s), probs, psum, child_begin, child_end)
+        return probs, psum, plan
+
     def slos_coefs(self, U: torch.Tensor, in_state) -> torch.Tensor:
         """Un-normalised SLOS coefficients of the last layer (what _Path.coefs holds, _slos.py:44)."""
         s = _state_u8(in_state)

@@ -331,3 +331,54 @@ def test_slos_kernel_variants_vs_oracle(env):
     assert out.returncode == 0, out.stderr[-2000:]
     worst = float(out.stdout.strip().split("WORST")[-1])
     assert worst < REL, (env, worst)
+
+
+# ---------------------------------------------------------------- recompute-window partition (segmented parents)
+
+@pytest.mark.parametrize("m,st,world,sub", [(16, (1,) * 8 + (0,) * 8, 3, 1), (12, (2, 1, 1, 0, 1, 1) + (0,) * 6, 4, 2),
+                                            (20, (1,) * 6 + (0,) * 14, 2, 3), (6, (1, 0, 2, 0, 1, 0), 5, 1)])
+def test_slos_windowed_chain_matches_full_distribution(eng, oracle, m, st, world, sub):
+    """Every (rank, sub-shard) of the recompute-window partition, run one after the other on this GPU, reproduces its slice
+    of the full distribution bit for bit (same kernels, same parent values), touches no parent outside its plan
+    (check_status) and the slices sum to 1."""
+    from perceval_b200 import dist as pdist, partition as P
+    u = oracle.random_unitary(m, seed=5)
+    U = eng.unitary(u)
+    full, _, _ = eng.slos_probs(U, st)
+    n = sum(st)
+    total = torch.zeros(1, dtype=torch.float64, device="cuda")
+    covered = 0
+    for rank in range(world):
+        for b, e, plan in pdist.windowed_plan(m, n, rank, world, sub):
+            probs, _, _ = eng.slos_probs_windowed(U, st, b, e, psum=total, plan=plan)
+            eng.check_status()
+            assert torch.equal(probs, full[b:e])
+            assert all(len(plan[k]) <= 2 for k in plan)
+            covered += e - b
+    assert covered == P.count(m, n)
+    assert abs(float(total.item()) - 1.0) < 1e-12
+
+
+def test_slos_segmented_parent_flags_missing_parents(eng, oracle):
+    """A parent inside the hole of a segmented window is an error, exactly like one outside the window."""
+    from perceval_b200 import partition as P
+    m, k = 10, 5
+    u = oracle.random_unitary(m, seed=6)
+    U = eng.unitary(u)
+    parent = eng.slos_coefs(U, (1, 1, 1, 1) + (0,) * 6)
+    Np, Nc = P.count(m, k - 1), P.count(m, k)
+    b, e = Nc // 2, Nc // 2 + 600
+    segs = P.parent_segments(m, k, [(b, e)], max_segments=2)
+    ref = eng.slos_layer(m, k, U, 4, parent, child_begin=b, child_end=e)
+    packed = torch.cat([parent[lo:hi] for lo, hi in segs])
+    out = torch.empty(e - b, dtype=torch.complex128, device="cuda")
+    eng.slos_layer_seg(m, k, U, 4, packed, segs, out, b, e)
+    eng.check_status()
+    assert torch.equal(out, ref)
+    # shrink the first segment: some needed parents are now missing
+    lo, hi = segs[0]
+    bad = [(lo + 7, hi)] + segs[1:]
+    packed_bad = torch.cat([parent[x:y] for x, y in bad])
+    eng.slos_layer_seg(m, k, U, 4, packed_bad, bad, out, b, e)
+    with pytest.raises(pb.FockError):
+        eng.check_status()

@@ -1,0 +1,98 @@
+"""Host-side planning of the recompute-window partition (perceval_b200/partition.py): exact parent sets of contiguous
+child ranges, against brute-force enumeration, and the chain executed with the CPU oracle as the compute step."""
+import random
+
+import numpy as np
+import pytest
+
+from perceval_b200 import partition as P
+
+
+def _brute_parents(m, k, b, e):
+    need = set()
+    for r in range(b, e):
+        s = P.unrank(m, k, r)
+        for j in range(m):
+            if s[j] > 0:
+                p = list(s)
+                p[j] -= 1
+                need.add(P.rank(m, p))
+    return need
+
+
+@pytest.mark.parametrize("m,k", [(3, 2), (4, 5), (6, 4), (5, 7), (8, 3), (7, 5), (2, 6), (1, 3)])
+def test_parent_segments_are_exact(m, k):
+    rng = random.Random(m * 100 + k)
+    N = P.count(m, k)
+    for _ in range(25):
+        b = rng.randrange(N)
+        e = rng.randrange(b + 1, N + 1)
+        need = _brute_parents(m, k, b, e)
+        exact = P.parent_segments(m, k, [(b, e)], max_segments=64)
+        assert set(x for lo, hi in exact for x in range(lo, hi)) == need
+        two = P.parent_segments(m, k, [(b, e)], max_segments=2)
+        assert len(two) <= 2 and need <= set(x for lo, hi in two for x in range(lo, hi))
+        for j in range(m):   # per mode: one contiguous range (the monotone bijection)
+            lo, hi = P.parent_range(m, k, b, e, j)
+            got = set()
+            for r in range(b, e):
+                s = P.unrank(m, k, r)
+                if s[j] > 0:
+                    p = list(s)
+                    p[j] -= 1
+                    got.add(P.rank(m, p))
+            assert got == set(range(lo, hi))
+
+
+def test_rank_unrank_agree_with_the_library():
+    from perceval_b200 import fsarray
+    for m, n in [(4, 5), (6, 4), (12, 6)]:
+        states = fsarray.enumerate_states(m, n)
+        for r in (0, 1, len(states) // 2, len(states) - 1):
+            assert P.unrank(m, n, r) == [int(x) for x in states[r]]
+            assert P.rank(m, [int(x) for x in states[r]]) == r
+        assert P.count(m, n) == len(states)
+
+
+def test_plan_memory_model_14_28():
+    """The flagship configuration fits: 16 sub-shards over 8 ranks keep the windowed chain under 150 GB per GPU."""
+    from perceval_b200 import dist as pdist
+    m, n = 28, 14
+    worst = max(pdist.windowed_peak_bytes(n, pdist.windowed_plan(m, n, r, 8, 2)) for r in range(8))
+    assert worst < 150e9
+    pieces = pdist.windowed_plan(m, n, 1, 8, 2)
+    assert all(len(plan[k]) <= 2 for _, _, plan in pieces for k in plan)
+
+
+def test_windowed_chain_with_the_oracle(oracle):
+    """The chain executed on packed, segmented layer buffers with the oracle's gather layer: every sub-shard equals its
+    slice of the reference distribution."""
+    m, st = 7, (1, 1, 0, 2, 0, 1, 0)
+    n = sum(st)
+    u = oracle.random_unitary(m, seed=8)
+    ref = oracle.slos_probs(u, st)
+    order = oracle.slos_order(st)
+    lib = oracle.lib()
+    N = P.count(m, n)
+    for world in (2, 3):
+        for r in range(world):
+            b, e = N * r // world, N * (r + 1) // world
+            plan = P.plan_chain(m, n, b, e)
+            layer = {0: np.ones(1, dtype=np.complex128)}
+            for k in range(1, n + 1):
+                full_parent = np.full(P.count(m, k - 1), np.nan + 0j, dtype=np.complex128)   # NaN marks "not resident"
+                off = 0
+                for lo, hi in plan[k - 1]:
+                    full_parent[lo:hi] = layer[k - 1][off:off + hi - lo]
+                    off += hi - lo
+                pieces = []
+                for lo, hi in plan[k]:
+                    child = np.empty(hi - lo, dtype=np.complex128)
+                    lib.orc_slos_layer_gather(m, k, oracle._p(oracle._u(u)), order[k - 1], oracle._p(full_parent), oracle._p(child), lo, hi)
+                    pieces.append(child)
+                layer[k] = np.concatenate(pieces)
+                assert not np.isnan(layer[k]).any()   # a missing parent would have propagated a NaN
+            states = oracle.unrank_batch(m, n, np.arange(b, e, dtype=np.uint64))
+            f = np.array([oracle.prodnfact(s) for s in states])
+            p = (np.abs(layer[n]) ** 2) * f / oracle.prodnfact(st)
+            assert np.abs(p - ref[b:e]).max() < 1e-14
