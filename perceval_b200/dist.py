@@ -145,49 +145,69 @@ def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1):
     return out
 
 
-def windowed_peak_bytes(n: int, pieces) -> int:
-    """Device bytes the windowed chain needs at its worst moment: the two packed layer buffers of one sub-shard plus the
-    probabilities of the sub-shards already finished (8 B each) -- see engine_slos_probs_windowed."""
+def windowed_buffer_elems(n: int, pieces):
+    """(A, B): complex128 elements of the two packed ping-pong layer buffers that serve every sub-shard of ``pieces``
+    (layers n-1, n-3, ... live in A, layers n-2, n-4, ... in B)."""
     from . import partition as P
-    worst, done = 0, 0
-    for b, e, plan in pieces:
-        a = max([P.segments_len(plan[k]) for k in range(n - 1, -1, -2)] + [1])
-        bb = max([P.segments_len(plan[k]) for k in range(n - 2, -1, -2)] + [1])
-        worst = max(worst, done + 16 * (a + bb), done + 16 * a + 8 * (e - b))
-        done += 8 * (e - b)
-    return worst
+    a = max([P.segments_len(plan[k]) for _, _, plan in pieces for k in range(n - 1, -1, -2)] + [1])
+    b = max([P.segments_len(plan[k]) for _, _, plan in pieces for k in range(n - 2, -1, -2)] + [1])
+    return a, b
 
 
-def engine_slos_probs_windowed(engine, U, in_state, group=None, sub: int | None = None, mem_fraction: float = 0.8):
+def windowed_peak_bytes(n: int, pieces) -> int:
+    """Device bytes of a WindowedChain: both layer buffers plus the probabilities of the rank's whole range."""
+    a, b = windowed_buffer_elems(n, pieces)
+    return 16 * (a + b) + 8 * sum(e - bb for bb, e, _ in pieces)
+
+
+class WindowedChain:
     """Recompute-window partition of the SLOS chain: NO exchange step.  Every rank owns a contiguous range of the output
     layer and recomputes, layer by layer, exactly the parents that range needs (one or two rank ranges per layer,
     partition.py), so no layer is ever replicated or gathered.  This is what lets 14 photons / 28 modes (layer 13 alone is
-    192 GB) run on 8 x 180 GB.  ``sub`` cuts the rank's range further to bound memory (None: smallest count whose peak
-    fits ``mem_fraction`` of the free device memory).  Returns (list of probability tensors, list of (begin, end),
-    total sum(p) tensor)."""
-    occ = [int(x) for x in in_state]
-    m, n = len(occ), sum(occ)
-    rank, world = _world(group)
-    if sub is None:
-        free, _total = torch.cuda.mem_get_info(engine.device)
-        sub = 1
-        while sub < 64 and windowed_peak_bytes(n, windowed_plan(m, n, rank, world, sub)) > mem_fraction * free:
-            sub += 1
-        if dist.is_available() and dist.is_initialized() and world > 1:   # same piece count everywhere keeps the ranges aligned
-            t = torch.tensor([sub], dtype=torch.int64, device=engine.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            sub = int(t.item())
-    pieces = windowed_plan(m, n, rank, world, sub)
-    psum = torch.zeros(1, dtype=torch.float64, device=engine.device)
-    outs, ranges = [], []
-    for b, e, plan in pieces:
-        probs, _, _ = engine.slos_probs_windowed(U, occ, b, e, psum=psum, plan=plan)
-        outs.append(probs)
-        ranges.append((b, e))
-        torch.cuda.empty_cache()   # the packed layer buffers of this piece are gone before the next piece allocates its own
-    if world > 1:
-        dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)
-    return outs, ranges, psum
+    192 GB) run on 8 x 180 GB.  The rank's range is cut in ``sub`` sub-shards processed one after the other to bound the
+    layer buffers (None: the smallest count whose workspace fits ``mem_fraction`` of the free device memory).  Buffers
+    and plans are built once; ``run(U)`` is one step."""
+
+    def __init__(self, engine, in_state, group=None, sub: int | None = None, mem_fraction: float = 0.85):
+        self.engine = engine
+        self.occ = [int(x) for x in in_state]
+        self.m, self.n = len(self.occ), sum(self.occ)
+        assert self.n >= 1
+        self.group = group
+        self.rank, self.world = _world(group)
+        if sub is None:
+            free, _total = torch.cuda.mem_get_info(engine.device)
+            sub = 1
+            while sub < 64 and windowed_peak_bytes(self.n, windowed_plan(self.m, self.n, self.rank, self.world, sub)) > mem_fraction * free:
+                sub += 1
+            if self.world > 1:   # the same piece count everywhere keeps the ranges aligned
+                t = torch.tensor([sub], dtype=torch.int64, device=engine.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                sub = int(t.item())
+        self.sub = sub
+        self.pieces = windowed_plan(self.m, self.n, self.rank, self.world, sub)
+        self.begin, self.end = self.pieces[0][0], self.pieces[-1][1]
+        a, b = windowed_buffer_elems(self.n, self.pieces)
+        self.bytes = windowed_peak_bytes(self.n, self.pieces)
+        self.buffers = (torch.empty(a, dtype=torch.complex128, device=engine.device),
+                        torch.empty(b, dtype=torch.complex128, device=engine.device))
+        self.probs = torch.empty(self.end - self.begin, dtype=torch.float64, device=engine.device)
+        self.psum = torch.zeros(1, dtype=torch.float64, device=engine.device)
+
+    def run(self, U, reduce_sum: bool = True, last_events: list | None = None):
+        """one step: returns (probabilities of [begin, end), (begin, end), sum(p) over all ranks)"""
+        self.psum.zero_()
+        for b, e, plan in self.pieces:
+            self.engine.slos_probs_windowed(U, self.occ, b, e, probs=self.probs[b - self.begin:e - self.begin], psum=self.psum,
+                                            plan=plan, buffers=self.buffers, last_events=last_events)
+        if reduce_sum and self.world > 1:
+            dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
+        return self.probs, (self.begin, self.end), self.psum
+
+
+def engine_slos_probs_windowed(engine, U, in_state, group=None, sub: int | None = None):
+    """One-shot form of WindowedChain."""
+    return WindowedChain(engine, in_state, group, sub).run(U)
 
 
 def permanents_sharded(perm_fn, mats: torch.Tensor, group=None):

@@ -170,7 +170,7 @@ class FockEngine:
         return probs
 
     def slos_probs_windowed(self, U: torch.Tensor, in_state, child_begin: int, child_end: int, probs: torch.Tensor | None = None,
-                            psum: torch.Tensor | None = None, plan=None, buffers=None):
+                            psum: torch.Tensor | None = None, plan=None, buffers=None, last_events: list | None = None):
         """Probabilities of the ranks [child_begin, child_end) of the output layer, keeping resident -- and computing --
         only the parents of every layer that this range needs (partition.plan_chain): the recompute-window partition
         of a multi-GPU run.  Returns (probs, psum, plan)."""
@@ -214,7 +214,13 @@ class FockEngine:
                 torch.cuda.synchronize(self.device)
                 torch.cuda.empty_cache()
             probs = torch.empty(child_end - child_begin, dtype=torch.float64, device=self.device)
+        if last_events is not None:   # CUDA events around the dominant launch (bench.py roofline)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         self.slos_layer_probs_seg(m, n, U, order[n - 1], parent, parent_segs, prodnfact(s), probs, psum, child_begin, child_end)
+        if last_events is not None:
+            ev[1].record()
+            last_events.append((ev[0], ev[1], 16 * P.segments_len(parent_segs) + 8 * (child_end - child_begin)))
         return probs, psum, plan
 
     def slos_coefs(self, U: torch.Tensor, in_state) -> torch.Tensor:
