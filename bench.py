@@ -192,6 +192,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- partition: replicated / gathered intermediate layers (default) or the recompute-window chain when they do not fit
+    partition = args.partition
+    if partition == "auto":
+        free, _tot = torch.cuda.mem_get_info(dev)
+        need = 16 * (eng.count(m, n - 1) + max(eng.count(m, n - 2), 1)) + 8 * (N // world + 1)
+        partition = "layers" if need < 0.9 * free else "windowed"
+    if partition == "windowed":
+        return run_b200_windowed(args, torch, dist, pdist, eng, U, u_host, in_state, world, rank, local_rank, barrier)
+
     # persistent workspaces (only two layers are ever live)
     b, e = pdist.shard_range(N, rank, world)
     probs = torch.empty(e - b, dtype=torch.float64, device=dev)
@@ -268,7 +277,7 @@ def run_b200(args):
     roofline = {"kernel": "SLOS last layer + fused |c|^2*prod(s!)/prod(in!) epilogue (csrc/slos.cu)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                "traffic": load_traffic("slos_last_layer_bytes"),
+                "traffic": load_traffic("slos_last_layer_bytes") if world == 1 else None,   # the ncu capture is of the whole layer
                 "whole_chain": {"algorithmic_bytes": sum(16.0 * (eng.count(m, k - 1) + eng.count(m, k)) for k in range(1, n))
                                 + 16.0 * eng.count(m, n - 1) + 8.0 * N,
                                 "note": "all layers, 16 B read+write per coefficient, last layer writes 8 B probabilities"}}
@@ -348,6 +357,104 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_windowed(args, torch, dist, pdist, eng, U, u_host, in_state, world, rank, local_rank, barrier):
+    """The same step through dist.WindowedChain: every rank recomputes exactly the parents its range of the output layer
+    needs (no exchange step, no replicated layer) -- the only partition that fits 14 photons / 28 modes on 8 x 180 GB."""
+    dev = eng.device
+    n, m = args.photons, args.modes
+    N = eng.count(m, n)
+    chain = pdist.WindowedChain(eng, in_state, sub=args.sub or None)
+    b, e = chain.begin, chain.end
+    for _ in range(max(args.warmup, 3)):
+        chain.run(U, reduce_sum=False)
+    barrier()
+    eng.check_status()
+    psum = chain.psum.clone()
+    if world > 1:
+        dist.all_reduce(psum)
+    total_p = float(psum.item())
+    assert abs(total_p - 1.0) < 1e-9, f"sum(p) = {total_p}"
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    events = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        chain.run(U, reduce_sum=False, last_events=events)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = eng.launch_count() - launches0
+    kernel_ms = sum(a.elapsed_time(c) for a, c, _ in events) / len(events)          # per last-layer launch
+    alg_bytes = sum(x for _, _, x in events) / len(events)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"kernel": "SLOS last layer + fused probability epilogue, one sub-shard, segmented parent (csrc/slos.cu, CHECK == 2)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "traffic": None}
+
+    # ---- end to end: U from pinned host memory, the rank's probabilities back to the host through a pinned ring
+    ring = [torch.empty(32 << 20, dtype=torch.float64).pin_memory() for _ in range(2)]   # 2 x 256 MB
+    side = torch.cuda.Stream(dev)
+
+    def e2e_step():
+        Ud = torch.empty_like(U)
+        Ud.copy_(u_host, non_blocking=True)
+        chain.run(Ud, reduce_sum=False)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        evs = [None, None]
+        with torch.cuda.stream(side):
+            for i, off in enumerate(range(0, e - b, ring[0].numel())):
+                buf = ring[i % 2]
+                if evs[i % 2] is not None:
+                    evs[i % 2].synchronize()      # the host consumer has released this ring slot
+                k = min(buf.numel(), e - b - off)
+                buf[:k].copy_(chain.probs[off:off + k], non_blocking=True)
+                evs[i % 2] = torch.cuda.Event()
+                evs[i % 2].record(side)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1) / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clk = clocks.stop()
+    e2e = {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(u_host.numel() * 16), "d2h_bytes_per_step": int((e - b) * 8),
+           "api": "U.copy_(pinned host U) + dist.WindowedChain.run + the rank's probabilities to the host through a 2 x 256 MB pinned ring"}
+    line = {"metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic",
+            "config": workload_config({"states": N, "photons": n, "modes": m,
+                                       "workload": f"SLOS full output distribution, {n} photons / {m} modes, Haar-random unitary seed 0, "
+                                                   f"input |1^{n},0^{m - n}>",
+                                       "l2_policy": "inputs larger than L2",
+                                       "partition": f"recompute-window: {world} ranks x {chain.sub} sub-shards, every rank recomputes the parents "
+                                                    f"its output range needs, no exchange step; workspace {chain.bytes / 1e9:.1f} GB on rank 0"}),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "sum_p": total_p}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def extras(eng, torch):
     """Single-GPU figures for the other BASELINE configs (permanents n=24 / n=30, C&C sampling 20 photons / 400 modes)."""
     from perceval_b200.circuit import random_unitary
@@ -402,6 +509,9 @@ def main():
     ap.add_argument("--modes", type=int, default=N_MODES)
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "replicate"])
     ap.add_argument("--e2e-pieces", type=int, default=8)
+    ap.add_argument("--partition", default="auto", choices=["auto", "layers", "windowed"],
+                    help="layers: replicate / all-gather the intermediate layers; windowed: recompute-window chain (no exchange)")
+    ap.add_argument("--sub", type=int, default=0, help="windowed: sub-shards per rank (0 = from free memory)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
