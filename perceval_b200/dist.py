@@ -133,14 +133,17 @@ def engine_slos_probs_sharded(engine, U, in_state, group=None, exchange: str = "
     return slos_probs_sharded(m, occ, order, engine.count, layer_fn, last_fn, group, exchange)
 
 
-def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1):
-    """Sub-shards of a rank in the recompute-window partition: the rank's contiguous range of the output layer is cut in
-    ``sub`` pieces, each with its own chain plan (partition.plan_chain).  Returns [(begin, end, plan), ...]."""
+def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1, balanced: bool = True):
+    """Sub-shards of a rank in the recompute-window partition: the output layer is cut in world * sub contiguous ranges
+    of about equal chain cost (partition.balanced_boundaries; equal counts if ``balanced`` is False), rank r takes the
+    ranges r*sub .. r*sub+sub-1, each with its own chain plan.  Returns [(begin, end, plan), ...]."""
     from . import partition as P
     N = P.count(m, n)
+    total = world * sub
+    bounds = P.balanced_boundaries(m, n, total) if balanced else [shard_range(N, i, total)[0] for i in range(total)] + [N]
     out = []
-    for i in range(sub):
-        b, e = shard_range(N, rank * sub + i, world * sub)
+    for i in range(rank * sub, rank * sub + sub):
+        b, e = bounds[i], bounds[i + 1]
         out.append((b, e, P.plan_chain(m, n, b, e)))
     return out
 
@@ -168,19 +171,22 @@ class WindowedChain:
     layer buffers (None: the smallest count whose workspace fits ``mem_fraction`` of the free device memory).  Buffers
     and plans are built once; ``run(U)`` is one step."""
 
-    def __init__(self, engine, in_state, group=None, sub: int | None = None, mem_fraction: float = 0.85):
+    def __init__(self, engine, in_state, group=None, sub: int | None = None, mem_fraction: float = 0.85, as_rank=None):
         self.engine = engine
         self.occ = [int(x) for x in in_state]
         self.m, self.n = len(self.occ), sum(self.occ)
         assert self.n >= 1
         self.group = group
         self.rank, self.world = _world(group)
+        emulated = as_rank is not None   # (rank, world) of a run emulated on this device alone (tools, tests): no collectives
+        if emulated:
+            self.rank, self.world = as_rank
         if sub is None:
             free, _total = torch.cuda.mem_get_info(engine.device)
             sub = 1
             while sub < 64 and windowed_peak_bytes(self.n, windowed_plan(self.m, self.n, self.rank, self.world, sub)) > mem_fraction * free:
                 sub += 1
-            if self.world > 1:   # the same piece count everywhere keeps the ranges aligned
+            if self.world > 1 and not emulated:   # the same piece count everywhere keeps the ranges aligned
                 t = torch.tensor([sub], dtype=torch.int64, device=engine.device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
                 sub = int(t.item())
@@ -193,6 +199,7 @@ class WindowedChain:
                         torch.empty(b, dtype=torch.complex128, device=engine.device))
         self.probs = torch.empty(self.end - self.begin, dtype=torch.float64, device=engine.device)
         self.psum = torch.zeros(1, dtype=torch.float64, device=engine.device)
+        self.emulated = emulated
 
     def run(self, U, reduce_sum: bool = True, last_events: list | None = None):
         """one step: returns (probabilities of [begin, end), (begin, end), sum(p) over all ranks)"""
@@ -200,7 +207,7 @@ class WindowedChain:
         for b, e, plan in self.pieces:
             self.engine.slos_probs_windowed(U, self.occ, b, e, probs=self.probs[b - self.begin:e - self.begin], psum=self.psum,
                                             plan=plan, buffers=self.buffers, last_events=last_events)
-        if reduce_sum and self.world > 1:
+        if reduce_sum and self.world > 1 and not self.emulated:
             dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
         return self.probs, (self.begin, self.end), self.psum
 

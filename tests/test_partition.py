@@ -97,3 +97,16 @@ def test_windowed_chain_with_the_oracle(oracle):
             f = np.array([oracle.prodnfact(s) for s in states])
             p = (np.abs(layer[n]) ** 2) * f / oracle.prodnfact(st)
             assert np.abs(p - ref[b:e]).max() < 1e-14
+
+
+@pytest.mark.parametrize("m,n,pieces", [(7, 5, 6), (12, 6, 8), (24, 12, 8)])
+def test_balanced_boundaries(m, n, pieces):
+    N = P.count(m, n)
+    bounds = P.balanced_boundaries(m, n, pieces)
+    assert bounds[0] == 0 and bounds[-1] == N and len(bounds) == pieces + 1
+    assert all(a < b for a, b in zip(bounds[:-1], bounds[1:]))
+    cost = [P.chain_cost(P.plan_chain(m, n, bounds[i], bounds[i + 1])) for i in range(pieces)]
+    equal = [N * i // pieces for i in range(pieces + 1)]
+    cost_eq = [P.chain_cost(P.plan_chain(m, n, equal[i], equal[i + 1])) for i in range(pieces)]
+    assert max(cost) / (sum(cost) / pieces) <= max(cost_eq) / (sum(cost_eq) / pieces) + 1e-9
+    assert bounds == P.balanced_boundaries(m, n, pieces)   # deterministic: every rank derives the same list
