@@ -206,12 +206,15 @@ __device__ __forceinline__ bool tile_win_load(const TileArgs &a, const double2 *
     return true;
 }
 
+#ifndef TILE_MINB
+#define TILE_MINB 2
+#endif
 #define TILE_VP 4   // prefix edges whose loads are issued together with the tail loads
 #define TILE_TB 8   // tail parents loaded per batch
 
 // CHECK: 0 = whole layers, 1 = child range only (sharded child, resident parent layer), 2 = child range + parent window
 template <int D, int MODE, int CHECK>
-__global__ void __launch_bounds__(TILE_BLOCK, 2) slos_tile_kernel(const __grid_constant__ TileArgs a) {
+__global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const __grid_constant__ TileArgs a) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     const int m = a.m, p = a.p, maxnz = a.maxnz;
     const int tid = threadIdx.x;
