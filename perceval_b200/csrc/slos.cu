@@ -825,6 +825,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_pipe_kernel(const __grid_c
 
 // ---------------------------------------------------------------- host side
 bool slos_mu_supports(int D, int k);
+bool slos_thin_supports(int D, int k);           // slos_thin.cu
+int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);                   // slos_mu.cu
 int slos_mu_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_blk_tail_modes(int m);                 // slos_blk.cu
@@ -963,12 +965,15 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     const bool full = (cb == 0 && ce == fock_count(m, k));
     uint64_t items = 0;
     int ncls = 0;
-    for (int w = 0; w <= k; ++w) {
+    // classes with small tail blocks first: their CTAs walk many prefixes with little work each and would otherwise run
+    // alone at the end of the grid
+    const int w_first = slos_env_int("FOCK_TILE_SMALL_FIRST", 1) ? k : 0, w_step = w_first ? -1 : 1;
+    for (int w = w_first; w >= 0 && w <= k; w += w_step) {
         const int u = k - w;
         if (u < u_from) continue;   // classes below u_from are handled by the block-staged kernel (slos_blk.cu)
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
-        if ((gfilter == 1 && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
+        if (((gfilter == 1 || gfilter == 3) && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
         uint64_t lo = 0, hi = np_total;
         if (!full) {
             // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
@@ -986,7 +991,9 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         tc.G = S64 >= TILE_BLOCK ? 1u : (uint32_t)(TILE_BLOCK / S64);
         tc.nchunks = S64 >= TILE_BLOCK ? (uint32_t)((S64 + TILE_BLOCK - 1) / TILE_BLOCK) : 1u;
         tc.rho_lo = lo; tc.np = hi - lo;
-        tc.per_item = (uint64_t)slos_env_int("FOCK_TILE_PERITEM", 512) * tc.G;
+        // prefixes per CTA: 128 sweep steps for full tiles (512: 21.0 ms, 128: 20.5 ms for the 12/24 chain -- mid-size layers need the CTAs); packed small tiles (G prefixes per step) get short items so that
+        // they spread over many CTAs instead of one CTA walking tens of thousands of prefixes
+        tc.per_item = (uint64_t)(tc.G > 1 ? slos_env_int("FOCK_TILE_PERITEM_SMALL", 32) : slos_env_int("FOCK_TILE_PERITEM", 128)) * tc.G;
         tc.item_begin = items;
         items += ((tc.np + tc.per_item - 1) / tc.per_item) * tc.nchunks;
     }
@@ -1008,6 +1015,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     const int check = !parent_whole ? 2 : (full ? 0 : 1);
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
     if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
+    if (gfilter == 3) return slos_thin_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
     // lean variant when the whole parent layer is resident (no parent-window checks needed)
     {
         static int use_lean = -1;
@@ -1095,9 +1103,14 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
         static int use_mu = -1;
         if (use_mu < 0) {
             const char *e = getenv("FOCK_SLOS_KERNEL");
-            use_mu = (e && !strcmp(e, "v4")) ? 1 : 0;
+            use_mu = (e && !strcmp(e, "v4")) ? 1 : ((e && !strcmp(e, "v5")) ? 2 : 0);
         }
-        if (D > 0 && use_mu && parent_full && slos_mu_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
+        if (D > 0 && use_mu == 2 && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
+            // v5 (slos_thin.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 3)) return rc;
+            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
+        }
+        if (D > 0 && use_mu == 1 && parent_full && slos_mu_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
             // v4 (slos_mu.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
             if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 1)) return rc;
             return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);

@@ -1,0 +1,274 @@
+// slos_thin.cu -- v5 "thin-thread" SLOS tile kernel (complex128, sm_100a).
+//
+// Same tiling and prefix sweep as slos_tile_kernel (slos.cu; replaces FSMap.compute_slos_layer, reference call site
+// perceval/backends/_slos.py:99, python twin :91-97, and xq.all_prob_normalize_output, _slos.py:199,213).  The
+// measurements of profiles/README.md ("what bounds the SLOS tile kernel") say the v2 kernel is limited by latency hiding:
+// 128 registers per thread leave 4 warps per scheduler to cover descriptor LDS -> address -> load -> FMA chain -> store.
+// This variant is built for <= 64 registers (8 warps per scheduler):
+//   * the per-thread tail offsets live in a shared-memory column (one LDS.32 per slot) instead of 16 registers;
+//   * tail slots are WARP-uniform: slot s of a warp is the s-th tail mode that any of its 32 lanes occupies, so the
+//     unitary entry of a slot is one broadcast LDS from a per-warp table (no per-lane look-up), a lane that does not
+//     occupy the mode keeps a zero in its landing registers (predicated load), and the FMAs carry no predicate;
+//   * loads are issued in groups of 4 (16 landing registers); the extra round trips are covered by the extra warps;
+//   * the sweep is specialised on the warp's slot count.
+// Accumulation order per child: prefix modes ascending, then tail modes ascending -- the order of v1 / v2 (a skipped mode
+// adds +0), so results are bit-identical.
+#include <stdlib.h>
+
+#include "slos_tile.cuh"
+
+#define TH_DB 128     // prefix descriptors per batch
+#define TH_GRP 4      // tail slots loaded together
+#define TH_ROWS 3     // prefix rows loaded up front
+
+#ifndef TH_MINB
+#define TH_MINB 4
+#endif
+
+int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);   // slos_mu.cu
+
+struct __align__(16) ThDesc {
+    uint64_t cbase;
+    const char *tptr;   // byte address of the tail-parent block of this prefix
+    double pfact;
+    int nz, pad;
+};
+
+__device__ __forceinline__ double th_factorial(int n) {
+    double f = 1.0;
+    for (int i = 2; i <= n; ++i) f *= (double)i;
+    return f;
+}
+__device__ __forceinline__ void th_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ double2 th_ldg(const char *p) { return __ldg((const double2 *)p); }
+
+struct ThShared {
+    double2 *s_u;       // [m] column mk of U
+    ThDesc *s_desc;     // [TH_DB]
+    double2 *e_u;       // [TH_DB][maxnz]
+    uint64_t *e_ptr;    // [TH_DB][maxnz]
+    double2 *s_uw;      // [8 warps][D]   unitary entry of slot s of the warp (zero beyond its slot count)
+    uint32_t *s_col;    // [D][TILE_BLOCK] byte offset of the tail parent of slot s for each thread
+};
+
+template <int D, int W, int MODE, bool RANGECHK>
+__device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, const uint32_t pm, const uint32_t t, const int u, const int w,
+                                         const uint64_t rho_a, const uint64_t rho_b, const double tfact, const bool active,
+                                         double &local_sum) {
+    const int m = a.m, p = a.p, maxnz = a.maxnz;
+    const int tid = threadIdx.x;
+    const uint64_t *__restrict__ bt = a.bt;
+    const uint64_t *__restrict__ dt = a.dt;
+    const char *__restrict__ parent_b = (const char *)a.parent;
+    const uint32_t t16 = t << 4;
+    const uint32_t *col = sh.s_col + tid;
+    const double2 *uw = sh.s_uw + (tid >> 5) * D;
+    for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += TH_DB) {
+        const int nb = (int)((rho_b - rho0) < (uint64_t)TH_DB ? (rho_b - rho0) : (uint64_t)TH_DB);
+        th_bar();
+        if (tid < nb) {   // cooperative prefix descriptors: thread i un-ranks prefix rho0 + i of FS(p, w)
+            uint64_t rem = rho0 + tid;
+            int Tprev = w;
+            uint64_t base = 0, E = 0;
+            int nz = 0;
+            double pf = 1.0;
+            for (int i = 0; i < p; ++i) {
+                int T = 0;
+                if (i < p - 1) {
+                    const uint64_t *row = bt + (p - 1 - i) * FOCK_TMAX;
+                    T = Tprev;
+                    while (__ldg(row + T) > rem) --T;
+                    rem -= __ldg(row + T);
+                }
+                const int si = Tprev - T;
+                const int Tfull = T + u;
+                if (si > 0) {
+                    sh.e_ptr[tid * maxnz + nz] = E;
+                    sh.e_u[tid * maxnz + nz] = sh.s_u[i];
+                    ++nz;
+                    pf *= th_factorial(si);
+                }
+                base += __ldg(bt + (m - 1 - i) * FOCK_TMAX + Tfull);
+                if (Tfull > 0) E += __ldg(dt + (m - 1 - i) * FOCK_TMAX + Tfull);
+                Tprev = T;
+            }
+            for (int e = 0; e < nz; ++e) sh.e_ptr[tid * maxnz + e] = (uint64_t)(parent_b + ((base - sh.e_ptr[tid * maxnz + e]) << 4));
+            ThDesc td;
+            td.cbase = base;
+            td.tptr = parent_b + ((base - E) << 4);
+            td.pfact = pf;
+            td.nz = nz;
+            td.pad = 0;
+            sh.s_desc[tid] = td;
+        }
+        th_bar();
+        if (!active) continue;
+#pragma unroll 1
+        for (int i = 0; i < nb; ++i) {
+            const ThDesc td = sh.s_desc[i];
+            const uint64_t r = td.cbase + t;
+            if (RANGECHK && (r < a.cbegin || r >= a.cend)) continue;
+            const uint64_t *ep = sh.e_ptr + i * maxnz;
+            const double2 *pu = sh.e_u + i * maxnz;
+            const int nz = td.nz;
+            // ---- prefix rows: the first TH_ROWS up front, the rest one by one
+            double2 pv[TH_ROWS];
+#pragma unroll
+            for (int e = 0; e < TH_ROWS; ++e)
+                if (e < nz) pv[e] = th_ldg((const char *)ep[e] + t16);
+            // ---- first group of tail slots: a lane that does not occupy the mode keeps zeros
+            double2 tv[TH_GRP];
+#pragma unroll
+            for (int s = 0; s < TH_GRP && s < W; ++s) {
+                tv[s] = make_double2(0.0, 0.0);
+                if (pm & (1u << s)) tv[s] = th_ldg(td.tptr + col[s * TILE_BLOCK]);
+            }
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int e = 0; e < TH_ROWS; ++e)
+                if (e < nz) acc = cfma(pu[e], pv[e], acc);
+            for (int e = TH_ROWS; e < nz; ++e) acc = cfma(pu[e], th_ldg((const char *)ep[e] + t16), acc);
+#pragma unroll
+            for (int s = 0; s < TH_GRP && s < W; ++s) acc = cfma(uw[s], tv[s], acc);
+#pragma unroll
+            for (int s0 = TH_GRP; s0 < W; s0 += TH_GRP) {
+#pragma unroll
+                for (int s = s0; s < s0 + TH_GRP && s < W; ++s) {
+                    tv[s - s0] = make_double2(0.0, 0.0);
+                    if (pm & (1u << s)) tv[s - s0] = th_ldg(td.tptr + col[s * TILE_BLOCK]);
+                }
+#pragma unroll
+                for (int s = s0; s < s0 + TH_GRP && s < W; ++s) acc = cfma(uw[s], tv[s - s0], acc);
+            }
+            if (MODE & 1) a.child[r - a.cbegin] = acc;
+            if (MODE & 2) {
+                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
+                __stcs(a.probs + (r - a.cbegin), pr);
+                local_sum += pr;
+            }
+        }
+    }
+}
+
+// Only classes whose tail block holds >= 256 states (G == 1) are handled here; the few small ones go to v2.
+template <int D, int MODE, bool RANGECHK>
+__global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin_kernel(const __grid_constant__ TileArgs a) {
+    extern __shared__ __align__(16) unsigned char th_smem[];
+    const int m = a.m, p = a.p, maxnz = a.maxnz;
+    const int tid = threadIdx.x;
+    ThShared sh;
+    sh.s_u = (double2 *)th_smem;
+    sh.s_desc = (ThDesc *)(sh.s_u + m);
+    sh.e_u = (double2 *)(sh.s_desc + TH_DB);
+    sh.e_ptr = (uint64_t *)(sh.e_u + TH_DB * maxnz);
+    sh.s_uw = (double2 *)(sh.e_ptr + TH_DB * maxnz);
+    sh.s_col = (uint32_t *)(sh.s_uw + (TILE_BLOCK / 32) * D);
+    __shared__ double s_red[TILE_BLOCK / 32];
+    const uint64_t *__restrict__ dt = a.dt;
+
+    for (int i = tid; i < m; i += TILE_BLOCK) sh.s_u[i] = a.U[(size_t)i * m + a.mk];
+    for (int i = tid; i < (TILE_BLOCK / 32) * D; i += TILE_BLOCK) sh.s_uw[i] = make_double2(0.0, 0.0);
+    int ci = 0;
+    for (int c = 1; c < a.ncls; ++c)
+        if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
+    const int w = a.cls[ci].w, u = a.cls[ci].u;
+    const uint32_t S = a.cls[ci].S, nchunks = a.cls[ci].nchunks;
+    const uint64_t local = (uint64_t)blockIdx.x - a.cls[ci].item_begin;
+    const uint32_t chunk = (uint32_t)(local % nchunks);
+    const uint64_t range = local / nchunks;
+    const uint64_t rho_a = a.cls[ci].rho_lo + range * a.cls[ci].per_item;
+    uint64_t rho_b = rho_a + a.cls[ci].per_item;
+    if (rho_b > a.cls[ci].rho_lo + a.cls[ci].np) rho_b = a.cls[ci].rho_lo + a.cls[ci].np;
+    __syncthreads();
+
+    // ---- per-thread tail set-up from the cached occupation tuple (slos_mu.cu): occupancy bits and parent offset per MODE
+    const uint32_t t = chunk * TILE_BLOCK + tid;
+    const bool active = t < S;
+    uint32_t occ = 0;       // bit i: tail mode i occupied
+    double tfact = 1.0;
+    uint64_t tup = 0;
+    if (active) tup = __ldg(a.tup[ci] + t);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+        if ((tup >> (4 * i)) & 15u) occ |= 1u << i;
+    const uint32_t wbits = __reduce_or_sync(0xffffffffu, occ);   // modes any lane of the warp occupies: the warp's slots
+    uint32_t pm = 0;        // bit s: this lane occupies the mode of slot s
+    {
+        uint32_t E = 0;
+        int T = u;
+        int slot = 0;
+        double2 *uw = sh.s_uw + (tid >> 5) * D;
+        const int lane = tid & 31;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const int si = (int)((tup >> (4 * i)) & 15u);
+            T -= si;
+            if (wbits & (1u << i)) {        // warp-uniform
+                if (si > 0) {
+                    sh.s_col[slot * TILE_BLOCK + tid] = (t - E) << 4;
+                    pm |= 1u << slot;
+                    if (si > 1) tfact *= th_factorial(si);
+                }
+                if (lane == 0) uw[slot] = sh.s_u[p + i];
+                ++slot;
+            }
+            if (active && i < D - 1 && T > 0) E += (uint32_t)__ldg(dt + (D - 1 - i) * FOCK_TMAX + T);
+        }
+    }
+    __syncwarp();
+    const int nslots = __popc(wbits);
+    double local_sum = 0.0;
+#define TH_SWEEP(WW) th_sweep<D, (WW) < D ? (WW) : D, MODE, RANGECHK>(a, sh, pm, t, u, w, rho_a, rho_b, tfact, active, local_sum)
+    if (nslots <= 4) TH_SWEEP(4);
+    else if (nslots <= 8) TH_SWEEP(8);
+    else if (nslots <= 12) TH_SWEEP(12);
+    else TH_SWEEP(16);
+#undef TH_SWEEP
+    if ((MODE & 2) && a.sum) {
+        local_sum = warp_sum(local_sum);
+        if ((tid & 31) == 0) s_red[tid >> 5] = local_sum;
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < TILE_BLOCK / 32 ? s_red[tid] : 0.0;
+            v = warp_sum(v);
+            if (tid == 0) atomicAdd(a.sum, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int D, int MODE, bool CHK>
+static int th_launch1(const TileArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
+    FOCK_CUDA(cudaFuncSetAttribute(slos_thin_kernel<D, MODE, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slos_thin_kernel<D, MODE, CHK><<<grid, TILE_BLOCK, smem, st>>>(a);
+    return fock_check_cuda(cudaGetLastError(), "slos_thin_kernel");
+}
+
+template <int D>
+static int th_launch(const TileArgs &a, bool wc, bool wp, bool chk, unsigned grid, size_t smem, cudaStream_t st) {
+    if (wp && wc) return chk ? th_launch1<D, 3, true>(a, grid, smem, st) : th_launch1<D, 3, false>(a, grid, smem, st);
+    if (wp) return chk ? th_launch1<D, 2, true>(a, grid, smem, st) : th_launch1<D, 2, false>(a, grid, smem, st);
+    return chk ? th_launch1<D, 1, true>(a, grid, smem, st) : th_launch1<D, 1, false>(a, grid, smem, st);
+}
+
+bool slos_thin_supports(int D, int k) { return (D == 12 || D == 16) && k <= 15; }
+
+// `a` is a finished work plan of slos_layer_tiles (slos.cu) holding only classes with G == 1; the whole parent layer must
+// be resident and 16-byte aligned.
+int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st) {
+    for (int i = 0; i < a.ncls; ++i)
+        if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
+    const size_t smem = (size_t)a.m * 16 + (size_t)TH_DB * sizeof(ThDesc) + (size_t)TH_DB * a.maxnz * 24 +
+                        (size_t)(TILE_BLOCK / 32) * D * 16 + (size_t)D * TILE_BLOCK * 4 + 16;
+    int rc;
+    switch (D) {
+        case 12: rc = th_launch<12>(a, want_child, want_probs, rangechk, grid, smem, st); break;
+        case 16: rc = th_launch<16>(a, want_child, want_probs, rangechk, grid, smem, st); break;
+        default:
+            fock_set_error("slos_thin: tail width %d not instantiated", D);
+            return FOCK_ERR_LIMIT;
+    }
+    if (rc) return rc;
+    c->launches++;
+    return FOCK_OK;
+}

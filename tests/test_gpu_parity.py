@@ -317,7 +317,7 @@ print("WORST", worst)
 
 @pytest.mark.parametrize("env", [{"FOCK_SLOS_KERNEL": "v1"}, {"FOCK_SLOS_KERNEL": "v3"}, {"FOCK_TILE_PIPE": "1"},
                                  {"FOCK_TILE_LEAN": "1"}, {"FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v4"},
-                                 {"FOCK_SLOS_KERNEL": "v4", "FOCK_SLOS_TAIL": "8"}])
+                                 {"FOCK_SLOS_KERNEL": "v4", "FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v5"}])
 def test_slos_kernel_variants_vs_oracle(env):
     # every kernel variant profiles/README.md quotes is held to the same 1e-10 bar as the default (the variant is chosen
     # once per process, hence the subprocess)
