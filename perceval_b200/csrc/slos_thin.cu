@@ -7,8 +7,9 @@
 // This variant is built for <= 64 registers (8 warps per scheduler):
 //   * the per-thread tail offsets live in a shared-memory column (one LDS.32 per slot) instead of 16 registers;
 //   * tail slots are WARP-uniform: slot s of a warp is the s-th tail mode that any of its 32 lanes occupies, so the
-//     unitary entry of a slot is one broadcast LDS from a per-warp table (no per-lane look-up), a lane that does not
-//     occupy the mode keeps a zero in its landing registers (predicated load), and the FMAs carry no predicate;
+//     unitary entry of a slot comes from the constant bank (column mk of U, indexed by the slot's mode from a per-warp
+//     packed list: no L1TEX wavefront, no per-lane look-up), a lane that does not occupy the mode keeps a zero in its
+//     landing registers (predicated load), and the FMAs carry no predicate;
 //   * loads are issued in groups of 4 (16 landing registers); the extra round trips are covered by the extra warps;
 //   * the sweep is specialised on the warp's slot count.
 // Accumulation order per child: prefix modes ascending, then tail modes ascending -- the order of v1 / v2 (a skipped mode
@@ -19,13 +20,19 @@
 
 #define TH_DB 128     // prefix descriptors per batch
 #define TH_GRP 4      // tail slots loaded together
-#define TH_ROWS 3     // prefix rows loaded up front
+#define TH_ROWS 2     // prefix rows loaded up front
 
 #ifndef TH_MINB
 #define TH_MINB 4
 #endif
 
 int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);   // slos_mu.cu
+
+// column mk of U in the constant bank (stream-ordered D2D copy before each launch): the unitary entry of a tail slot is
+// warp-uniform, so it is fetched through the constant cache (LDC: no L1TEX wavefront, no LSU write-back) with the slot's
+// mode read from a per-warp packed list.  (Doing the same for the prefix rows, or specialising the sweep on more slot
+// counts, measured slower: 13.0 ms / 18.9 ms vs 12.45 ms for the last 12/24 layer.)
+__constant__ double2 c_th_u[FOCK_QMAX];
 
 struct __align__(16) ThDesc {
     uint64_t cbase;
@@ -47,12 +54,12 @@ struct ThShared {
     ThDesc *s_desc;     // [TH_DB]
     double2 *e_u;       // [TH_DB][maxnz]
     uint64_t *e_ptr;    // [TH_DB][maxnz]
-    double2 *s_uw;      // [8 warps][D]   unitary entry of slot s of the warp (zero beyond its slot count)
     uint32_t *s_col;    // [D][TILE_BLOCK] byte offset of the tail parent of slot s for each thread
 };
 
 template <int D, int W, int MODE, bool RANGECHK>
-__device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, const uint32_t pm, const uint32_t t, const int u, const int w,
+__device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, const uint32_t pm, const uint32_t wm_lo, const uint32_t wm_hi,
+                                         const uint32_t t, const int u, const int w,
                                          const uint64_t rho_a, const uint64_t rho_b, const double tfact, const bool active,
                                          double &local_sum) {
     const int m = a.m, p = a.p, maxnz = a.maxnz;
@@ -62,7 +69,8 @@ __device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, 
     const char *__restrict__ parent_b = (const char *)a.parent;
     const uint32_t t16 = t << 4;
     const uint32_t *col = sh.s_col + tid;
-    const double2 *uw = sh.s_uw + (tid >> 5) * D;
+    const int pbase = p;
+#define TH_U(s) c_th_u[pbase + ((((s) < 8 ? wm_lo : wm_hi) >> (4 * ((s) & 7))) & 15u)]
     for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += TH_DB) {
         const int nb = (int)((rho_b - rho0) < (uint64_t)TH_DB ? (rho_b - rho0) : (uint64_t)TH_DB);
         th_bar();
@@ -129,7 +137,7 @@ __device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, 
                 if (e < nz) acc = cfma(pu[e], pv[e], acc);
             for (int e = TH_ROWS; e < nz; ++e) acc = cfma(pu[e], th_ldg((const char *)ep[e] + t16), acc);
 #pragma unroll
-            for (int s = 0; s < TH_GRP && s < W; ++s) acc = cfma(uw[s], tv[s], acc);
+            for (int s = 0; s < TH_GRP && s < W; ++s) acc = cfma(TH_U(s), tv[s], acc);
 #pragma unroll
             for (int s0 = TH_GRP; s0 < W; s0 += TH_GRP) {
 #pragma unroll
@@ -138,16 +146,18 @@ __device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, 
                     if (pm & (1u << s)) tv[s - s0] = th_ldg(td.tptr + col[s * TILE_BLOCK]);
                 }
 #pragma unroll
-                for (int s = s0; s < s0 + TH_GRP && s < W; ++s) acc = cfma(uw[s], tv[s - s0], acc);
+                for (int s = s0; s < s0 + TH_GRP && s < W; ++s) acc = cfma(TH_U(s), tv[s - s0], acc);
             }
             if (MODE & 1) a.child[r - a.cbegin] = acc;
             if (MODE & 2) {
-                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
+                const double tf = __hiloint2double((int)col[(D + 1) * TILE_BLOCK], (int)col[D * TILE_BLOCK]);   // prod tail s! of this thread
+                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tf);
                 __stcs(a.probs + (r - a.cbegin), pr);
                 local_sum += pr;
             }
         }
     }
+#undef TH_U
 }
 
 // Only classes whose tail block holds >= 256 states (G == 1) are handled here; the few small ones go to v2.
@@ -161,13 +171,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin_kernel(const __
     sh.s_desc = (ThDesc *)(sh.s_u + m);
     sh.e_u = (double2 *)(sh.s_desc + TH_DB);
     sh.e_ptr = (uint64_t *)(sh.e_u + TH_DB * maxnz);
-    sh.s_uw = (double2 *)(sh.e_ptr + TH_DB * maxnz);
-    sh.s_col = (uint32_t *)(sh.s_uw + (TILE_BLOCK / 32) * D);
+    sh.s_col = (uint32_t *)(sh.e_ptr + TH_DB * maxnz);
     __shared__ double s_red[TILE_BLOCK / 32];
     const uint64_t *__restrict__ dt = a.dt;
 
     for (int i = tid; i < m; i += TILE_BLOCK) sh.s_u[i] = a.U[(size_t)i * m + a.mk];
-    for (int i = tid; i < (TILE_BLOCK / 32) * D; i += TILE_BLOCK) sh.s_uw[i] = make_double2(0.0, 0.0);
     int ci = 0;
     for (int c = 1; c < a.ncls; ++c)
         if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
@@ -193,12 +201,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin_kernel(const __
         if ((tup >> (4 * i)) & 15u) occ |= 1u << i;
     const uint32_t wbits = __reduce_or_sync(0xffffffffu, occ);   // modes any lane of the warp occupies: the warp's slots
     uint32_t pm = 0;        // bit s: this lane occupies the mode of slot s
+    uint32_t wm_lo = 0, wm_hi = 0;   // tail mode of slot s, 4 bits each (warp-uniform); unused slots -> mode 0, never occupied
     {
         uint32_t E = 0;
         int T = u;
         int slot = 0;
-        double2 *uw = sh.s_uw + (tid >> 5) * D;
-        const int lane = tid & 31;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             const int si = (int)((tup >> (4 * i)) & 15u);
@@ -209,16 +216,19 @@ __global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin_kernel(const __
                     pm |= 1u << slot;
                     if (si > 1) tfact *= th_factorial(si);
                 }
-                if (lane == 0) uw[slot] = sh.s_u[p + i];
+                if (slot < 8) wm_lo |= (uint32_t)i << (4 * slot);
+                else wm_hi |= (uint32_t)i << (4 * (slot - 8));
                 ++slot;
             }
             if (active && i < D - 1 && T > 0) E += (uint32_t)__ldg(dt + (D - 1 - i) * FOCK_TMAX + T);
         }
     }
+    sh.s_col[D * TILE_BLOCK + tid] = (uint32_t)__double2loint(tfact);        // kept in shared memory: two registers fewer in the sweep
+    sh.s_col[(D + 1) * TILE_BLOCK + tid] = (uint32_t)__double2hiint(tfact);
     __syncwarp();
     const int nslots = __popc(wbits);
     double local_sum = 0.0;
-#define TH_SWEEP(WW) th_sweep<D, (WW) < D ? (WW) : D, MODE, RANGECHK>(a, sh, pm, t, u, w, rho_a, rho_b, tfact, active, local_sum)
+#define TH_SWEEP(WW) th_sweep<D, (WW) < D ? (WW) : D, MODE, RANGECHK>(a, sh, pm, wm_lo, wm_hi, t, u, w, rho_a, rho_b, tfact, active, local_sum)
     if (nslots <= 4) TH_SWEEP(4);
     else if (nslots <= 8) TH_SWEEP(8);
     else if (nslots <= 12) TH_SWEEP(12);
@@ -258,8 +268,11 @@ bool slos_thin_supports(int D, int k) { return (D == 12 || D == 16) && k <= 15; 
 int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st) {
     for (int i = 0; i < a.ncls; ++i)
         if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
+    static void *sym = nullptr;
+    if (!sym) FOCK_CUDA(cudaGetSymbolAddress(&sym, c_th_u));
+    FOCK_CUDA(cudaMemcpy2DAsync(sym, 16, a.U + a.mk, (size_t)a.m * 16, 16, (size_t)a.m, cudaMemcpyDeviceToDevice, st));
     const size_t smem = (size_t)a.m * 16 + (size_t)TH_DB * sizeof(ThDesc) + (size_t)TH_DB * a.maxnz * 24 +
-                        (size_t)(TILE_BLOCK / 32) * D * 16 + (size_t)D * TILE_BLOCK * 4 + 16;
+                        (size_t)(D + 2) * TILE_BLOCK * 4 + 16;
     int rc;
     switch (D) {
         case 12: rc = th_launch<12>(a, want_child, want_probs, rangechk, grid, smem, st); break;
