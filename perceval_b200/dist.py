@@ -133,14 +133,15 @@ def engine_slos_probs_sharded(engine, U, in_state, group=None, exchange: str = "
     return slos_probs_sharded(m, occ, order, engine.count, layer_fn, last_fn, group, exchange)
 
 
-def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1, balanced: bool = True):
+def windowed_plan(m: int, n: int, rank: int, world: int, sub: int = 1, balanced: bool = True, last_weight: float | None = None):
     """Sub-shards of a rank in the recompute-window partition: the output layer is cut in world * sub contiguous ranges
     of about equal chain cost (partition.balanced_boundaries; equal counts if ``balanced`` is False), rank r takes the
     ranges r*sub .. r*sub+sub-1, each with its own chain plan.  Returns [(begin, end, plan), ...]."""
     from . import partition as P
     N = P.count(m, n)
     total = world * sub
-    bounds = P.balanced_boundaries(m, n, total) if balanced else [shard_range(N, i, total)[0] for i in range(total)] + [N]
+    lw = P.LAST_LAYER_WEIGHT if last_weight is None else last_weight
+    bounds = P.balanced_boundaries(m, n, total, last_weight=lw) if balanced else [shard_range(N, i, total)[0] for i in range(total)] + [N]
     out = []
     for i in range(rank * sub, rank * sub + sub):
         b, e = bounds[i], bounds[i + 1]
@@ -181,17 +182,24 @@ class WindowedChain:
         emulated = as_rank is not None   # (rank, world) of a run emulated on this device alone (tools, tests): no collectives
         if emulated:
             self.rank, self.world = as_rank
-        if sub is None:
-            free, _total = torch.cuda.mem_get_info(engine.device)
-            sub = 1
-            while sub < 64 and windowed_peak_bytes(self.n, windowed_plan(self.m, self.n, self.rank, self.world, sub)) > mem_fraction * free:
-                sub += 1
-            if self.world > 1 and not emulated:   # the same piece count everywhere keeps the ranges aligned
-                t = torch.tensor([sub], dtype=torch.int64, device=engine.device)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-                sub = int(t.item())
+        from . import partition as P
+        # candidates in order of expected speed: fewer sub-shards recompute less; the time-weighted balance (output-layer
+        # states cost ~3x) is faster but gives the middle ranks wider windows than the state-count balance
+        cands = [(sub, w) for w in (P.LAST_LAYER_WEIGHT, 1.0)] if sub is not None else \
+                [(s_, w) for s_ in range(1, 65) for w in (P.LAST_LAYER_WEIGHT, 1.0)]
+        free, _total = torch.cuda.mem_get_info(engine.device)
+        pick = len(cands) - 1
+        for i, (s_, w) in enumerate(cands):
+            if windowed_peak_bytes(self.n, windowed_plan(self.m, self.n, self.rank, self.world, s_, last_weight=w)) <= mem_fraction * free:
+                pick = i
+                break
+        if self.world > 1 and not emulated:   # the same choice everywhere keeps the ranges aligned
+            t = torch.tensor([pick], dtype=torch.int64, device=engine.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            pick = int(t.item())
+        sub, self.last_weight = cands[pick]
         self.sub = sub
-        self.pieces = windowed_plan(self.m, self.n, self.rank, self.world, sub)
+        self.pieces = windowed_plan(self.m, self.n, self.rank, self.world, sub, last_weight=self.last_weight)
         self.begin, self.end = self.pieces[0][0], self.pieces[-1][1]
         a, b = windowed_buffer_elems(self.n, self.pieces)
         self.bytes = windowed_peak_bytes(self.n, self.pieces)

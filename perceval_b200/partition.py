@@ -141,7 +141,7 @@ def chain_cost(plan: dict, last_weight: float = LAST_LAYER_WEIGHT) -> float:
 
 
 @lru_cache(maxsize=64)
-def _balanced_boundaries(m: int, n: int, pieces: int, iterations: int, damping: float) -> tuple:
+def _balanced_boundaries(m: int, n: int, pieces: int, iterations: int, damping: float, last_weight: float) -> tuple:
     """Boundaries x_0 = 0 < ... < x_pieces = N(n) of contiguous output ranges whose chain costs (chain_cost) are about
     equal: equal-count ranges differ by 2.6x in cost at 14 photons / 28 modes because the parents of a range in the
     middle of the layer are spread wider.  Deterministic (every rank computes the same list)."""
@@ -150,7 +150,7 @@ def _balanced_boundaries(m: int, n: int, pieces: int, iterations: int, damping: 
     if pieces <= 1 or N < 4 * pieces:
         return tuple(bounds)
     for _ in range(iterations):
-        costs = [max(chain_cost(plan_chain(m, n, bounds[i], bounds[i + 1])), 1) for i in range(pieces)]
+        costs = [max(chain_cost(plan_chain(m, n, bounds[i], bounds[i + 1]), last_weight), 1) for i in range(pieces)]
         target = sum(costs) / pieces
         widths = [(bounds[i + 1] - bounds[i]) * (target / costs[i]) ** damping for i in range(pieces)]
         scale = N / sum(widths)
@@ -163,8 +163,9 @@ def _balanced_boundaries(m: int, n: int, pieces: int, iterations: int, damping: 
     return tuple(bounds)
 
 
-def balanced_boundaries(m: int, n: int, pieces: int, iterations: int = 8, damping: float = 0.7) -> list:
-    return list(_balanced_boundaries(m, n, pieces, iterations, damping))
+def balanced_boundaries(m: int, n: int, pieces: int, iterations: int = 8, damping: float = 0.7,
+                        last_weight: float = LAST_LAYER_WEIGHT) -> list:
+    return list(_balanced_boundaries(m, n, pieces, iterations, damping, float(last_weight)))
 
 
 def segments_len(segs) -> int:
