@@ -164,6 +164,33 @@ def windowed_peak_bytes(n: int, pieces) -> int:
     return 16 * (a + b) + 8 * sum(e - bb for bb, e, _ in pieces)
 
 
+def windowed_candidates(sub: int | None = None):
+    """(sub-shards per rank, balance weight) in order of expected speed: fewer sub-shards recompute less; the time-weighted
+    balance (output-layer states cost ~3x) is faster but gives the middle ranks wider windows than the state-count one."""
+    from . import partition as P
+    subs = [sub] if sub is not None else list(range(1, 65))
+    return [(s_, w) for s_ in subs for w in (P.LAST_LAYER_WEIGHT, 1.0)]
+
+
+def windowed_pick(m: int, n: int, rank: int, world: int, free_bytes: int, mem_fraction: float = 0.85, sub: int | None = None,
+                  group=None, collective: bool = True) -> tuple:
+    """First candidate whose workspace fits ``mem_fraction * free_bytes`` on this rank, then the LAST such index over all
+    ranks (all-reduce MAX) so that every rank cuts the output layer at the same boundaries."""
+    cands = windowed_candidates(sub)
+    pick = len(cands) - 1
+    for i, (s_, w) in enumerate(cands):
+        if windowed_peak_bytes(n, windowed_plan(m, n, rank, world, s_, last_weight=w)) <= mem_fraction * free_bytes:
+            pick = i
+            break
+    if collective and world > 1 and dist.is_available() and dist.is_initialized():
+        t = torch.tensor([pick], dtype=torch.int64)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        pick = int(t.item())
+    return cands[pick]
+
+
 class WindowedChain:
     """Recompute-window partition of the SLOS chain: NO exchange step.  Every rank owns a contiguous range of the output
     layer and recomputes, layer by layer, exactly the parents that range needs (one or two rank ranges per layer,
@@ -182,22 +209,9 @@ class WindowedChain:
         emulated = as_rank is not None   # (rank, world) of a run emulated on this device alone (tools, tests): no collectives
         if emulated:
             self.rank, self.world = as_rank
-        from . import partition as P
-        # candidates in order of expected speed: fewer sub-shards recompute less; the time-weighted balance (output-layer
-        # states cost ~3x) is faster but gives the middle ranks wider windows than the state-count balance
-        cands = [(sub, w) for w in (P.LAST_LAYER_WEIGHT, 1.0)] if sub is not None else \
-                [(s_, w) for s_ in range(1, 65) for w in (P.LAST_LAYER_WEIGHT, 1.0)]
         free, _total = torch.cuda.mem_get_info(engine.device)
-        pick = len(cands) - 1
-        for i, (s_, w) in enumerate(cands):
-            if windowed_peak_bytes(self.n, windowed_plan(self.m, self.n, self.rank, self.world, s_, last_weight=w)) <= mem_fraction * free:
-                pick = i
-                break
-        if self.world > 1 and not emulated:   # the same choice everywhere keeps the ranges aligned
-            t = torch.tensor([pick], dtype=torch.int64, device=engine.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            pick = int(t.item())
-        sub, self.last_weight = cands[pick]
+        sub, self.last_weight = windowed_pick(self.m, self.n, self.rank, self.world, free, mem_fraction, sub, group,
+                                              collective=not emulated)
         self.sub = sub
         self.pieces = windowed_plan(self.m, self.n, self.rank, self.world, sub, last_weight=self.last_weight)
         self.begin, self.end = self.pieces[0][0], self.pieces[-1][1]

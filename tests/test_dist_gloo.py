@@ -103,3 +103,70 @@ def test_shard_range_and_exchange_model():
             assert max(sizes) - min(sizes) <= 1
     assert pdist.choose_exchange(10, 30, 1) == "replicate"
     assert pdist.choose_exchange(286097760, 834451800, 8) in ("replicate", "allgather")
+
+
+def _windowed_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from perceval_b200 import dist as pdist, partition as P
+
+    m, in_state = 8, (1, 1, 0, 1, 1, 0, 1, 0)
+    n = sum(in_state)
+    N = P.count(m, n)
+    # rank 1 pretends to have very little memory: both ranks must end up with ITS (later) candidate
+    free = 10 ** 12 if rank == 0 else 9000   # 0.85 * 9000 = 7650 B: rank 1 only fits from (3, 3.0) on (7344 B)
+    sub, weight = pdist.windowed_pick(m, n, rank, world, free, mem_fraction=0.85)
+    alone = pdist.windowed_pick(m, n, rank, world, free, mem_fraction=0.85, collective=False)
+    picks = [None] * world
+    dist.all_gather_object(picks, (sub, weight, alone))
+    assert picks[0][:2] == picks[1][:2], picks
+    assert picks[0][2] == (1, P.LAST_LAYER_WEIGHT) and picks[1][2] != picks[0][2], picks   # the tight rank forced the choice
+    pieces = pdist.windowed_plan(m, n, rank, world, sub, last_weight=weight)
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (pieces[0][0], pieces[-1][1]))
+    assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == N
+
+    # run the chain of every sub-shard with the oracle's gather layer on packed, segmented buffers
+    u = oracle.random_unitary(m, seed=9)
+    ref = oracle.slos_probs(u, in_state)
+    order = oracle.slos_order(in_state)
+    lib = oracle.lib()
+    psum = 0.0
+    for b, e, plan in pieces:
+        layer = {0: np.ones(1, dtype=np.complex128)}
+        for k in range(1, n + 1):
+            full_parent = np.full(P.count(m, k - 1), np.nan + 0j, dtype=np.complex128)
+            off = 0
+            for lo, hi in plan[k - 1]:
+                full_parent[lo:hi] = layer[k - 1][off:off + hi - lo]
+                off += hi - lo
+            parts = []
+            for lo, hi in plan[k]:
+                child = np.empty(hi - lo, dtype=np.complex128)
+                lib.orc_slos_layer_gather(m, k, oracle._p(oracle._u(u)), order[k - 1], oracle._p(full_parent), oracle._p(child), lo, hi)
+                parts.append(child)
+            layer[k] = np.concatenate(parts)
+        states = oracle.unrank_batch(m, n, np.arange(b, e, dtype=np.uint64))
+        f = np.array([oracle.prodnfact(s) for s in states])
+        p = (np.abs(layer[n]) ** 2) * f / oracle.prodnfact(in_state)
+        assert np.abs(p - ref[b:e]).max() < 1e-14
+        psum += float(p.sum())
+    t = torch.tensor([psum], dtype=torch.float64)
+    dist.all_reduce(t)
+    assert abs(t.item() - 1.0) < 1e-12
+    open(os.path.join(outdir, f"wok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_world2_windowed_partition_agreement(tmp_path):
+    """Recompute-window partition at world size 2 (gloo): the (sub-shards, balance) choice is agreed by all-reduce even when
+    the ranks see different free memory, the ranges tile the output layer, every sub-shard chain reproduces its slice and
+    the all-reduced sum(p) is 1."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_windowed_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"wok{r}")) for r in range(world))
