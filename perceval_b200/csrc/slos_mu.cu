@@ -1,16 +1,15 @@
-// slos_mu.cu -- v4 "mode-uniform" SLOS tile kernel (complex128, sm_100a).
+// slos_mu.cu -- (1) cached tail occupation tables shared by every SLOS tile kernel, (2) the v4 warp-specialised tile kernel.
 //
-// Same tiling and prefix sweep as slos_tile_kernel (slos.cu; replaces FSMap.compute_slos_layer, reference call site
-// perceval/backends/_slos.py:99, python twin :91-97, and xq.all_prob_normalize_output, _slos.py:199,213), with the tail
-// phase turned from a per-thread compacted edge list into a walk over the D tail MODES in fixed order:
-//   * the unitary entry of tail mode i is the same for every thread, so it is read from the constant bank as an
-//     immediate operand of the DFMA (no shared-memory look-up with a per-lane address, which cost the v2 kernel as many
-//     L1TEX wavefronts as the parent loads themselves);
-//   * a thread keeps one byte offset per tail mode (0 when the mode is empty) and a D-bit occupancy mask; empty modes are
-//     predicated off;
-//   * prefix rows are streamed with L1::no_allocate so they do not evict the tail-parent block, which is the only data
-//     with reuse inside the SM.
-// Rounding sequence (one accumulator, modes in ascending order) is the one of v1 / v2: results are bit-identical.
+// (1) mu_tuple_kernel / slos_mu_tuples: for a tail width D and a tail photon count u, entry t of the table is the
+//     occupation of the D tail modes of tail rank t in FS(D, u), 4 bits per mode.  The tables depend on (D, u) only, so
+//     they are built once per context and serve every layer, unitary and call; the tile kernels (slos.cu v2 -- the
+//     default --, v4 here, v5 in slos_thin.cu) read 8 bytes per thread instead of un-ranking their tail by search.
+// (2) slos_mu_kernel (FOCK_SLOS_KERNEL=v4, parity-tested, not the default): same tiling, prefix sweep and rounding
+//     sequence as slos_tile_kernel (replaces FSMap.compute_slos_layer, reference call site perceval/backends/_slos.py:99,
+//     python twin :91-97, and xq.all_prob_normalize_output, _slos.py:199,213); the sweep is specialised per warp on the
+//     number of tail slots it executes, the unitary entry of a slot is one LDS at a pre-computed shared address, and
+//     unused slots are neutralised by a zero coefficient instead of predicates (28 % fewer instructions, same speed:
+//     profiles/README.md).  FOCK_MU_DEBUG switches off parts of its memory traffic for timing experiments only.
 #include <stdlib.h>
 
 #include "slos_tile.cuh"
