@@ -275,7 +275,7 @@ def run_b200(args):
     alg_bytes = 16.0 * eng.count(m, n - 1) + 8.0 * (e - b)  # parent layer read once + this rank's probabilities written once
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"kernel": "SLOS last layer + fused |c|^2*prod(s!)/prod(in!) epilogue (csrc/slos.cu)",
+    roofline = {"kernel": "SLOS last layer + fused |c|^2*prod(s!)/prod(in!) epilogue (slos_thin6_kernel, csrc/slos_thin.cu, + the small-tile classes in slos_tile_kernel, csrc/slos.cu)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
                 "traffic": load_traffic("slos_last_layer_bytes") if world == 1 else None,   # the ncu capture is of the whole layer

@@ -826,7 +826,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2) slos_pipe_kernel(const __grid_c
 // ---------------------------------------------------------------- host side
 bool slos_mu_supports(int D, int k);
 bool slos_thin_supports(int D, int k);           // slos_thin.cu
-int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
+int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st,
+                     bool hybrid);
 int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);                   // slos_mu.cu
 int slos_mu_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_blk_tail_modes(int m);                 // slos_blk.cu
@@ -973,7 +974,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         if (u < u_from) continue;   // classes below u_from are handled by the block-staged kernel (slos_blk.cu)
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
-        if (((gfilter == 1 || gfilter == 3) && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
+        if (((gfilter == 1 || gfilter == 3 || gfilter == 4) && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
         uint64_t lo = 0, hi = np_total;
         if (!full) {
             // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
@@ -1015,7 +1016,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     const int check = !parent_whole ? 2 : (full ? 0 : 1);
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
     if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
-    if (gfilter == 3) return slos_thin_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
+    if (gfilter == 3 || gfilter == 4) return slos_thin_launch(c, D, a, wc, wp, !full, (unsigned)items, st, gfilter == 4);
     // lean variant when the whole parent layer is resident (no parent-window checks needed)
     {
         static int use_lean = -1;
@@ -1103,11 +1104,16 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
         static int use_mu = -1;
         if (use_mu < 0) {
             const char *e = getenv("FOCK_SLOS_KERNEL");
-            use_mu = (e && !strcmp(e, "v4")) ? 1 : ((e && !strcmp(e, "v5")) ? 2 : 0);
+            use_mu = (e && !strcmp(e, "v4")) ? 1 : ((e && !strcmp(e, "v5")) ? 2 : ((e && !strcmp(e, "v6")) ? 3 : ((e && !strcmp(e, "v2")) ? -2 : 0)));
         }
-        if (D > 0 && use_mu == 2 && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
-            // v5 (slos_thin.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
-            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 3)) return rc;
+        // default policy: the hybrid thin kernel (v6, slos_thin.cu) for large probability layers with at most 8 prefix modes
+        // (measured: last 12/24 layer 12.2 ms vs 13.5 ms with v2; with more prefix rows per child -- 13/26 -- or on the smaller
+        // coefficient layers v2 is faster); FOCK_SLOS_KERNEL=v2 / v4 / v5 / v6 forces one kernel
+        const bool auto_v6 = use_mu == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
+        if (D > 0 && (use_mu == 2 || use_mu == 3 || auto_v6) && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
+            // v5 / v6 (slos_thin.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
+            const int gf = (use_mu == 2) ? 3 : 4;
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gf)) return rc;
             return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
         }
         if (D > 0 && use_mu == 1 && parent_full && slos_mu_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {

@@ -317,7 +317,7 @@ print("WORST", worst)
 
 @pytest.mark.parametrize("env", [{"FOCK_SLOS_KERNEL": "v1"}, {"FOCK_SLOS_KERNEL": "v3"}, {"FOCK_TILE_PIPE": "1"},
                                  {"FOCK_TILE_LEAN": "1"}, {"FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v4"},
-                                 {"FOCK_SLOS_KERNEL": "v4", "FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v5"}])
+                                 {"FOCK_SLOS_KERNEL": "v4", "FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v5"}, {"FOCK_SLOS_KERNEL": "v6"}, {"FOCK_SLOS_KERNEL": "v2"}])
 def test_slos_kernel_variants_vs_oracle(env):
     # every kernel variant profiles/README.md quotes is held to the same 1e-10 bar as the default (the variant is chosen
     # once per process, hence the subprocess)
@@ -382,3 +382,30 @@ def test_slos_segmented_parent_flags_missing_parents(eng, oracle):
     eng.slos_layer_seg(m, k, U, 4, packed_bad, bad, out, b, e)
     with pytest.raises(pb.FockError):
         eng.check_status()
+
+
+def test_large_probability_layer_default_kernel_sharded(eng, oracle):
+    """11 photons / 22 modes (1.3e8 states): the probability layer goes through the default large-layer kernel (hybrid
+    thin kernel for <= 8 prefix modes), whole and in three rank ranges; the reference is the coefficient chain (plain tile
+    kernel) followed by the stand-alone epilogue, which share no code with it."""
+    from perceval_b200.engine import prodnfact
+    m, n = 22, 11
+    st = (1,) * n + (0,) * (m - n)
+    U = eng.unitary(oracle.random_unitary(m, seed=2))
+    order = eng.slos_order(st)
+    parent = torch.ones(1, dtype=torch.complex128, device="cuda")
+    for k in range(1, n):
+        parent = eng.slos_layer(m, k, U, order[k - 1], parent)
+    coefs = eng.slos_layer(m, n, U, order[n - 1], parent)
+    ref, s_ref = eng.slos_probs_from_coefs(m, n, coefs, prodnfact(st))
+    del coefs
+    N = ref.numel()
+    psum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    full = eng.slos_layer_probs(m, n, U, order[n - 1], parent, prodnfact(st), psum=psum)
+    assert float((full - ref).abs().max() / ref.max()) < 1e-12
+    assert abs(float(psum.item()) - 1.0) < 1e-12 and abs(float(s_ref.item()) - 1.0) < 1e-12
+    cuts = [0, N // 3 + 11, 2 * N // 3 - 7, N]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        part = eng.slos_layer_probs(m, n, U, order[n - 1], parent, prodnfact(st), child_begin=b, child_end=e)
+        assert torch.equal(part, full[b:e])
+    eng.check_status()
