@@ -499,8 +499,14 @@ int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want
     g_th_hybrid = (hybrid && D == 16) ? 1 : 0;
     for (int i = 0; i < a.ncls; ++i)
         if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
-    static void *sym = nullptr;
-    if (!sym) FOCK_CUDA(cudaGetSymbolAddress(&sym, c_th_u));
+    // The unitary column lives in ONE __constant__ symbol per device: a launch on another stream must not overwrite it
+    // while the previous kernel still reads it, so every launch waits for the previous one (a no-op on the same stream).
+    static cudaEvent_t last_done[64] = {};
+    void *sym = nullptr;
+    FOCK_CUDA(cudaGetSymbolAddress(&sym, c_th_u));
+    FOCK_REQUIRE(c->device >= 0 && c->device < 64, FOCK_ERR_LIMIT, "slos_thin: device index %d", c->device);
+    if (!last_done[c->device]) FOCK_CUDA(cudaEventCreateWithFlags(&last_done[c->device], cudaEventDisableTiming));
+    else FOCK_CUDA(cudaStreamWaitEvent(st, last_done[c->device], 0));
     FOCK_CUDA(cudaMemcpy2DAsync(sym, 16, a.U + a.mk, (size_t)a.m * 16, 16, (size_t)a.m, cudaMemcpyDeviceToDevice, st));
     const size_t smem = (size_t)a.m * 16 + (size_t)TH_DB * sizeof(ThDesc) + (size_t)TH_DB * a.maxnz * 24 +
                         (size_t)(D + 2) * TILE_BLOCK * 4 + 16;
@@ -513,6 +519,7 @@ int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want
             return FOCK_ERR_LIMIT;
     }
     if (rc) return rc;
+    FOCK_CUDA(cudaEventRecord(last_done[c->device], st));
     c->launches++;
     return FOCK_OK;
 }
