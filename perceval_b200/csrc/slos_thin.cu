@@ -135,7 +135,12 @@ __device__ __forceinline__ void th_sweep(const TileArgs &a, const ThShared &sh, 
 #pragma unroll
             for (int e = 0; e < TH_ROWS; ++e)
                 if (e < nz) acc = cfma(pu[e], pv[e], acc);
-            for (int e = TH_ROWS; e < nz; ++e) acc = cfma(pu[e], th_ldg((const char *)ep[e] + t16), acc);
+            for (int e = TH_ROWS; e < nz; e += 2) {   // further rows two at a time (one round trip per pair)
+                pv[0] = th_ldg((const char *)ep[e] + t16);
+                if (e + 1 < nz) pv[1] = th_ldg((const char *)ep[e + 1] + t16);
+                acc = cfma(pu[e], pv[0], acc);
+                if (e + 1 < nz) acc = cfma(pu[e + 1], pv[1], acc);
+            }
 #pragma unroll
             for (int s = 0; s < TH_GRP && s < W; ++s) acc = cfma(TH_U(s), tv[s], acc);
 #pragma unroll
@@ -330,7 +335,12 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const ThShared &sh,
 #pragma unroll
             for (int e = 0; e < TH_ROWS; ++e)
                 if (e < nz) acc = cfma(pu[e], pv[e], acc);
-            for (int e = TH_ROWS; e < nz; ++e) acc = cfma(pu[e], th_ldg((const char *)ep[e] + t16), acc);
+            for (int e = TH_ROWS; e < nz; e += 2) {   // further rows two at a time (one round trip per pair)
+                pv[0] = th_ldg((const char *)ep[e] + t16);
+                if (e + 1 < nz) pv[1] = th_ldg((const char *)ep[e + 1] + t16);
+                acc = cfma(pu[e], pv[0], acc);
+                if (e + 1 < nz) acc = cfma(pu[e + 1], pv[1], acc);
+            }
 #pragma unroll
             for (int s = 0; s < 4 && s < WL; ++s) acc = cfma(c_th_u[p + ((wm_lo >> (4 * s)) & 15u)], tv[s], acc);
             if (WL > 4) {
