@@ -57,8 +57,9 @@ int fock_enumerate(fock_ctx *ctx, int m, int n, uint64_t begin, uint64_t end, ui
  *      perceval/backends/_abstract_backends.py:130-137 ; perceval/simulators/simulator.py:650-662 ;
  *      tests/utils/test_mask.py:32-45) -------------------------------------------------------------------- */
 /* h_conds: nmask x m int8, -1 = any count, v >= 0 = exactly v photons (">= v" on modes whose bit is set in
- * at_least_bits); a state matches if it matches any mask.  allow_missing != 0 is the partial match of intermediate
- * layers.  d_flags[i] = 1 iff state #(begin+i) of FSArray(m,n) matches.  Synchronises `stream`. */
+ * at_least_bits); a state matches if it matches any mask.  allow_missing: 0 = exact match; 1 = the partial match of
+ * intermediate layers (a mode passes if its count can still grow into the condition); 2 + b = partial match that can still
+ * be completed with b more photons (what xq.FSArray(m, k, mask) keeps on layer k = n - b, _slos.py:156-166).  d_flags[i] = 1 iff state #(begin+i) of FSArray(m,n) matches.  Synchronises `stream`. */
 int fock_mask_match(fock_ctx *ctx, int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
                     uint64_t begin, uint64_t end, uint8_t *d_flags, void *stream);
 int fock_mask_match_host(int m, int n, const int8_t *h_conds, int nmask, uint64_t at_least_bits, int allow_missing,
@@ -90,6 +91,16 @@ int slos_layer_probs_seg(fock_ctx *ctx, int m, int k, const double *d_U, int mk,
                          const uint64_t *h_parent_seg, double *d_child, double *d_probs, double *d_sum, double in_prodnfact,
                          uint64_t child_begin, uint64_t child_end, void *stream);
 
+/* One layer over a PRUNED rank space (masks / heralds; replaces the layers the reference builds on xq.FSArray(m, k, mask),
+ * perceval/backends/_slos.py:156-166): d_child_ranks / d_parent_ranks are the ascending kept ranks of FSArray(m, k) /
+ * FSArray(m, k-1), d_parent the packed parent coefficients in that order.  Writes, per kept child, any of: the packed
+ * coefficient (d_child), the probability |c|^2 prod(s!)/in_prodnfact (d_probs, + atomic sum into d_sum), the amplitude
+ * c sqrt(prod(s!)/in_prodnfact) (d_amps) -- NULL skips an output.  A kept child whose parent is not in the parent list is an
+ * error reported through fock_check_status. */
+int slos_layer_masked(fock_ctx *ctx, int m, int k, const double *d_U, int mk, const uint64_t *d_parent_ranks, uint64_t n_parent,
+                      const double *d_parent, const uint64_t *d_child_ranks, uint64_t n_child, double *d_child, double *d_probs,
+                      double *d_amps, double *d_sum, double in_prodnfact, void *stream);
+
 /* Stand-alone epilogues on an existing coefficient range [begin,end) of FSArray(m,n). */
 int slos_probs_epilogue(fock_ctx *ctx, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,
                         double *d_sum, uint64_t begin, uint64_t end, void *stream);
@@ -103,7 +114,7 @@ int slos_order(int m, const uint8_t *h_in_state, int *h_order);
 /* Whole chain for one input state with caller-provided ping-pong device workspaces:
  * d_work_a must hold count(m,n-1) complex (0 if n==0), d_work_b count(m,n-2) complex; writes count(m,n) probs
  * (and coefficients if d_coefs != NULL).  Replaces SLOSBackend.set_input_state + prob_distribution/all_prob
- * (perceval/backends/_slos.py:143-145,195-214) for the single-input chain. */
+ * (perceval/backends/_slos.py:143-145,195-214) for the single-input chain.  Asynchronous on `stream`. */
 int slos_prob_distribution(fock_ctx *ctx, int m, const double *d_U, const uint8_t *h_in_state, double *d_work_a,
                            double *d_work_b, double *d_coefs, double *d_probs, double *d_sum, void *stream);
 /* Same call with HOST buffers (U in, probabilities out); allocates device workspaces internally, synchronous. */

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfock_b200.so")
-SOURCES = ["capi.cu", "slos.cu", "slos_mu.cu", "slos_thin.cu", "slos_blk.cu", "permanent.cu", "cc2017.cu", "peaks.cu"]
+SOURCES = ["capi.cu", "slos.cu", "slos_mu.cu", "slos_thin.cu", "slos_masked.cu", "permanent.cu", "cc2017.cu", "peaks.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "slos_tile.cuh"), os.path.join(os.path.dirname(HERE), "include", "fock_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

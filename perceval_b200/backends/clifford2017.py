@@ -24,11 +24,18 @@ def set_seed(seed: int | None):
 
 
 class Clifford2017B200Backend(ASamplingBackend):
-    def __init__(self, device=None, seed: int | None = None):
+    def __init__(self, device=None, seed: int | None = None, prefetch: int = 0):
+        """``prefetch``: draw at least this many samples per kernel launch and serve later ``samples()`` calls from the
+        device-side pool.  Perceval's sampling loop never asks for more than 1000 samples at once
+        (simulators/noisy_sampling_simulator.py:232; SamplesProvider pools <= 2000, :52), far below what fills a B200; since
+        sample i of the stream depends on (seed, i) only, the samples handed out are bit-identical with and without a pool."""
         super().__init__()
         self._device = device
         self._engine: FockEngine | None = None
         self._u_dev = None
+        self._prefetch = int(prefetch)
+        self._pool = None
+        self._pool_pos = 0
         if seed is None:
             seed = _global_seed
         # python's RNG is what pcvl.random_seed() seeds first (perceval/utils/_random.py:36-58)
@@ -46,17 +53,43 @@ class Clifford2017B200Backend(ASamplingBackend):
 
     def set_circuit(self, circuit):
         super().set_circuit(circuit)
-        self._u_dev = self._eng().unitary(np.asarray(self._umat, dtype=np.complex128))
+        self._u_dev = self._eng().unitary(self._umat)
+        self._pool = None
 
     def set_input_state(self, input_state):
         super().set_input_state(input_state)
+        self._pool = None
 
     def samples_tensor(self, count: int) -> torch.Tensor:
-        """(count, m) uint8 device tensor of occupation numbers."""
+        """(count, m) uint8 device tensor of occupation numbers: samples [drawn, drawn + count) of the stream."""
         assert self._input_state is not None, "Input state must be set before sampling"
-        out = self._eng().cc2017_samples(self._u_dev, [int(x) for x in self._input_state], int(count), self._seed, self._drawn)
-        self._drawn += int(count)
-        return out
+        count = int(count)
+        occ = [int(x) for x in self._input_state]
+        if self._prefetch <= count:
+            if self._pool is not None and self._pool_pos < self._pool.shape[0]:
+                head = self._pool[self._pool_pos:self._pool_pos + count]      # pooled samples come first: same stream order
+                self._pool_pos += head.shape[0]
+                self._drawn += head.shape[0]
+                if head.shape[0] == count:
+                    return head
+                rest = self._eng().cc2017_samples(self._u_dev, occ, count - head.shape[0], self._seed, self._drawn)
+                self._drawn += count - head.shape[0]
+                return torch.cat([head, rest])
+            out = self._eng().cc2017_samples(self._u_dev, occ, count, self._seed, self._drawn)
+            self._drawn += count
+            return out
+        parts, need = [], count
+        while need > 0:
+            if self._pool is None or self._pool_pos >= self._pool.shape[0]:
+                # the pool always starts at the next undrawn index of the stream
+                self._pool = self._eng().cc2017_samples(self._u_dev, occ, self._prefetch, self._seed, self._drawn)
+                self._pool_pos = 0
+            take = self._pool[self._pool_pos:self._pool_pos + need]
+            self._pool_pos += take.shape[0]
+            self._drawn += take.shape[0]
+            need -= take.shape[0]
+            parts.append(take)
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
 
     def sample(self):
         return self.samples(1)[0]

@@ -38,7 +38,7 @@ class NaiveB200Backend(AStrongSimulationBackend):
 
     def set_circuit(self, circuit):
         super().set_circuit(circuit)
-        self._u_dev = self._eng().unitary(np.asarray(self._umat, dtype=np.complex128))
+        self._u_dev = self._eng().unitary(self._umat)
 
     def prob_amplitude(self, output_state) -> complex:
         istate = self._input_state

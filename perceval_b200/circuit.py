@@ -10,8 +10,13 @@ class UnitaryCircuit:
     requires_polarization = False
 
     def __init__(self, u, name: str = "U"):
-        u = np.asarray(u, dtype=np.complex128)
-        assert u.ndim == 2 and u.shape[0] == u.shape[1], "unitary must be square"
+        """``u``: numpy array (or anything np.asarray accepts) -- or a torch tensor, host (pinned) or device, which the
+        backends take as it is (a device tensor makes ``set_circuit`` copy nothing)."""
+        if type(u).__module__.startswith("torch"):
+            assert u.dim() == 2 and u.shape[0] == u.shape[1], "unitary must be square"
+        else:
+            u = np.asarray(u, dtype=np.complex128)
+            assert u.ndim == 2 and u.shape[0] == u.shape[1], "unitary must be square"
         self._u = u
         self.name = name
 
@@ -19,7 +24,7 @@ class UnitaryCircuit:
     def m(self) -> int:
         return self._u.shape[0]
 
-    def compute_unitary(self, use_symbolic: bool = False, **kwargs) -> np.ndarray:
+    def compute_unitary(self, use_symbolic: bool = False, **kwargs):
         return self._u
 
     @property

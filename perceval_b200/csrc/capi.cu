@@ -74,6 +74,9 @@ extern "C" uint64_t fock_count(int m, int n) {
 }
 
 // ---------------------------------------------------------------- context
+void slos_mu_init(fock_ctx *c);      // slos_mu.cu
+void slos_mu_destroy(fock_ctx *c);
+void slos_thin_destroy(fock_ctx *c); // slos_thin.cu
 extern "C" int fock_create(int device, fock_ctx **out) {
     FOCK_REQUIRE(out != nullptr, FOCK_ERR_ARG, "fock_create: out is NULL");
     int ndev = 0;
@@ -91,13 +94,23 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     c->cc_minor = prop.minor;
     c->total_mem = prop.totalGlobalMem;
     c->launches = 0;
-    c->blk_state = nullptr;
     c->mu_state = nullptr;
+    slos_mu_init(c);
+    {   // keep stream-ordered scratch (StreamScratch) in the pool between calls
+        cudaMemPool_t pool;
+        uint64_t keep = UINT64_MAX;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     size_t tb = sizeof(uint64_t) * FOCK_QMAX * FOCK_TMAX;
     FOCK_CUDA(cudaMalloc(&c->d_bt, tb));
     FOCK_CUDA(cudaMalloc(&c->d_dt, tb));
     FOCK_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
     FOCK_CUDA(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
+    FOCK_CUDA(cudaMalloc(&c->d_vacuum, 2 * sizeof(double)));
+    {
+        const double one[2] = {1.0, 0.0};
+        FOCK_CUDA(cudaMemcpy(c->d_vacuum, one, sizeof one, cudaMemcpyHostToDevice));
+    }
     FOCK_CUDA(cudaMemcpy(c->d_bt, fock_host_bt(), tb, cudaMemcpyHostToDevice));
     FOCK_CUDA(cudaMemcpy(c->d_dt, fock_host_dt(), tb, cudaMemcpyHostToDevice));
     FOCK_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
@@ -105,18 +118,17 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     return FOCK_OK;
 }
 
-void slos_blk_destroy(fock_ctx *c);   // slos_blk.cu
-void slos_mu_destroy(fock_ctx *c);
 
 extern "C" int fock_destroy(fock_ctx *c) {
     if (!c) return FOCK_OK;
     ScopedDevice sd(c->device);
-    slos_blk_destroy(c);
     slos_mu_destroy(c);
+    slos_thin_destroy(c);
     cudaFree(c->d_bt);
     cudaFree(c->d_dt);
     cudaFree(c->d_status);
     cudaFree(c->d_scratch);
+    cudaFree(c->d_vacuum);
     delete c;
     return FOCK_OK;
 }
@@ -290,18 +302,24 @@ extern "C" int fock_enumerate(fock_ctx *c, int m, int n, uint64_t begin, uint64_
 #define FOCK_MASK_MAXCOND 2048
 __constant__ signed char c_mask_cond[FOCK_MASK_MAXCOND];
 
+// allow_missing: 0 exact match, 1 the reference's partial match, 2 + b partial match that can still be completed with b more
+// photons (the conditioned modes lack sum max(0, c_i - v_i) photons; pruned SLOS layers, slos_masked.cu)
 __host__ __device__ inline bool mask_match_one(const uint8_t *st, int m, const signed char *cond, int nmask, uint64_t at_least_bits, int allow_missing) {
     for (int k = 0; k < nmask; ++k) {
         const signed char *cd = cond + k * m;
         bool ok = true;
+        int deficit = 0;
         for (int i = 0; i < m && ok; ++i) {
             const int c = cd[i];
             if (c < 0) continue;
             const int v = st[i];
             const bool ge = i < 64 && ((at_least_bits >> i) & 1ull);
-            if (allow_missing) ok = ge || v <= c;
-            else ok = ge ? (v >= c) : (v == c);
+            if (allow_missing) {
+                ok = ge || v <= c;
+                if (v < c) deficit += c - v;
+            } else ok = ge ? (v >= c) : (v == c);
         }
+        if (ok && allow_missing >= 2 && deficit > allow_missing - 2) ok = false;
         if (ok) return true;
     }
     return false;
@@ -344,6 +362,8 @@ extern "C" int fock_mask_match(fock_ctx *c, int m, int n, const int8_t *h_conds,
     if (begin == end) return FOCK_OK;
     ScopedDevice sd(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    static std::mutex mask_lock;   // one constant-bank copy of the conditions per device: calls are serialised (each ends in a sync)
+    std::lock_guard<std::mutex> guard(mask_lock);
     FOCK_CUDA(cudaMemcpyToSymbolAsync(c_mask_cond, h_conds, (size_t)nmask * m, 0, cudaMemcpyHostToDevice, st));
     mask_match_kernel<<<grid_for(c, end - begin, 256), 256, 0, st>>>(m, n, c->d_bt, nmask, at_least_bits, allow_missing, begin, end - begin, d_flags);
     c->launches++;

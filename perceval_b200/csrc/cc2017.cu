@@ -221,13 +221,6 @@ __global__ void __launch_bounds__(CC_BLOCK) cc2017_kernel(const CcArgs a) {
     }
 }
 
-struct CcScratch {
-    void *buf = nullptr;
-    size_t cap = 0;
-    int device = -1;
-};
-static thread_local CcScratch g_cc;
-
 template <int H>
 static int launch_cc(fock_ctx *c, const CcArgs &a, cudaStream_t st) {
     const int NP = 4 * H;
@@ -266,14 +259,10 @@ extern "C" int cc2017_samples(fock_ctx *c, int m, int n, const double *d_U, cons
         return FOCK_OK;
     }
     const size_t bytes = 16 * (size_t)n * m + 256;
-    if (g_cc.device != c->device || g_cc.cap < bytes) {
-        if (g_cc.buf) cudaFree(g_cc.buf);
-        g_cc.buf = nullptr; g_cc.cap = 0;
-        FOCK_CUDA(cudaMalloc(&g_cc.buf, bytes));
-        g_cc.cap = bytes; g_cc.device = c->device;
-    }
-    double2 *At = (double2 *)g_cc.buf;
-    int *d_cols = (int *)((char *)g_cc.buf + 16 * (size_t)n * m);
+    StreamScratch scratch;   // gathered input columns, stream-ordered
+    if (int rc = scratch.alloc(bytes, st)) return rc;
+    double2 *At = (double2 *)scratch.ptr;
+    int *d_cols = (int *)((char *)scratch.ptr + 16 * (size_t)n * m);
     FOCK_CUDA(cudaMemcpyAsync(d_cols, cols, sizeof(int) * n, cudaMemcpyHostToDevice, st));
     cc_gather_columns_kernel<<<(n * m + 255) / 256, 256, 0, st>>>(m, n, (const double2 *)d_U, d_cols, At);
     c->launches++;

@@ -19,9 +19,9 @@ struct fock_ctx {
     uint64_t *d_bt;   // [FOCK_QMAX][FOCK_TMAX]  Bt[q][T] = C(T-1+q, q), 0 for T==0, saturating
     uint64_t *d_dt;   // [FOCK_QMAX][FOCK_TMAX]  Dt[q][T] = Bt[q][T]-Bt[q][T-1]
     int *d_status;    // device-side error flag
-    double *d_scratch; // small scratch (sum accumulators)
+    double *d_scratch; // small scratch (peaks.cu sinks)
+    double *d_vacuum;  // constant complex 1 + 0i: SLOS layer 0 (the vacuum coefficient), written once at creation
     uint64_t launches;
-    void *blk_state;   // owned by slos_blk.cu (column tables, cached layer plans)
     void *mu_state;    // owned by slos_mu.cu (cached tail occupation tables)
 };
 
@@ -53,6 +53,21 @@ struct ScopedDevice {
     }
     ~ScopedDevice() {
         if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Stream-ordered scratch memory: allocated and released on the caller's stream (cudaMallocAsync / cudaFreeAsync from the
+// device's default pool, whose release threshold fock_create raises so that the memory is re-used, not returned).  Calls
+// on different streams or host threads therefore never share a scratch buffer, and no call synchronises the device.
+struct StreamScratch {
+    void *ptr = nullptr;
+    cudaStream_t st = nullptr;
+    int alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        return fock_check_cuda(cudaMallocAsync(&ptr, bytes ? bytes : 16, s), "cudaMallocAsync");
+    }
+    ~StreamScratch() {
+        if (ptr) cudaFreeAsync(ptr, st);
     }
 };
 

@@ -146,27 +146,6 @@ __global__ void perm_trivial_kernel(int n, const double2 *__restrict__ mats, uin
 }
 
 // ---------------------------------------------------------------- dispatch
-struct GlynnScratch {
-    double2 *buf = nullptr;
-    size_t cap = 0;
-    int device = -1;
-};
-static thread_local GlynnScratch g_scratch;
-
-static int ensure_scratch(fock_ctx *c, size_t elems, double2 **out) {
-    if (g_scratch.device != c->device || g_scratch.cap < elems) {
-        if (g_scratch.buf) cudaFree(g_scratch.buf);
-        g_scratch.buf = nullptr;
-        g_scratch.cap = 0;
-        size_t want = elems < 4096 ? 4096 : elems;
-        FOCK_CUDA(cudaMalloc(&g_scratch.buf, want * sizeof(double2)));
-        g_scratch.cap = want;
-        g_scratch.device = c->device;
-    }
-    *out = g_scratch.buf;
-    return 0;
-}
-
 template <int N>
 static int launch_glynn(fock_ctx *c, const double2 *mats, uint64_t B, double2 *out, uint64_t g0, uint64_t g1, cudaStream_t st) {
     const uint64_t G = g1 - g0;
@@ -190,8 +169,9 @@ static int launch_glynn(fock_ctx *c, const double2 *mats, uint64_t B, double2 *o
     const uint64_t blocks_x = (nchunks + GLYNN_BLOCK - 1) / GLYNN_BLOCK;
     FOCK_REQUIRE(blocks_x < (1u << 31), FOCK_ERR_LIMIT, "glynn: too many chunks");
     const unsigned gy = (unsigned)(B < 32768 ? B : 32768);
-    double2 *partials = nullptr;
-    if (int rc = ensure_scratch(c, (size_t)B * blocks_x, &partials)) return rc;
+    StreamScratch scratch;   // per-call partial sums, stream-ordered
+    if (int rc = scratch.alloc((size_t)B * blocks_x * sizeof(double2), st)) return rc;
+    double2 *partials = (double2 *)scratch.ptr;
     dim3 grid((unsigned)blocks_x, gy);
     glynn_big_kernel<N><<<grid, GLYNN_BLOCK, 0, st>>>(mats, B, partials, g0, g1, chunk_log2);
     c->launches++;
@@ -305,13 +285,6 @@ __global__ void naive_scale_kernel(int n, uint64_t B, const double2 *__restrict_
     amps[b] = p;
 }
 
-struct NaiveScratch {
-    void *buf = nullptr;
-    size_t cap = 0;
-    int device = -1;
-};
-static thread_local NaiveScratch g_nscratch;
-
 static int naive_impl(fock_ctx *c, int m, int n, const double *d_U, const uint8_t *in_state, const uint64_t *d_ranks,
                       const uint8_t *d_states, uint64_t B, double *d_amps, void *stream) {
     FOCK_REQUIRE(c && d_U && in_state && d_amps && (d_ranks || d_states), FOCK_ERR_ARG, "naive_amplitudes: bad argument");
@@ -333,13 +306,9 @@ static int naive_impl(fock_ctx *c, int m, int n, const double *d_U, const uint8_
     const int nsq = n > 0 ? n * n : 1;
     // scratch: mats (B*n*n complex) | perms (B complex) | out_fact (B double) | in_cols (32 int)
     const size_t bytes = 16 * (size_t)B * nsq + 16 * B + 8 * B + 256;
-    if (g_nscratch.device != c->device || g_nscratch.cap < bytes) {
-        if (g_nscratch.buf) cudaFree(g_nscratch.buf);
-        g_nscratch.buf = nullptr; g_nscratch.cap = 0;
-        FOCK_CUDA(cudaMalloc(&g_nscratch.buf, bytes));
-        g_nscratch.cap = bytes; g_nscratch.device = c->device;
-    }
-    char *base = (char *)g_nscratch.buf;
+    StreamScratch scratch;
+    if (int rc = scratch.alloc(bytes, st)) return rc;
+    char *base = (char *)scratch.ptr;
     double2 *mats = (double2 *)base;
     double2 *perms = (double2 *)(base + 16 * (size_t)B * nsq);
     double *ofact = (double *)(base + 16 * (size_t)B * nsq + 16 * B);

@@ -19,11 +19,6 @@
 
 #define SLOS_BLOCK 256
 
-static int slos_env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 struct SlosArgs {
     int m, k, mk;
     const uint64_t *bt, *dt;
@@ -446,394 +441,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
     }
 }
 
-// ================================================================================================================
-// Lean tile kernel (v2d): the tiling and sweep of slos_tile_kernel with the per-edge instruction count cut down --
-// descriptors carry ready-made byte addresses (row base / tail-block base), tail offsets are pre-scaled to bytes, the U
-// entry of an occupied tail mode is one byte-extract + one LDS, unused tail lanes load a harmless valid address instead
-// of being predicated, and prefix loads branch on the CTA-uniform edge count.  Same rounding sequence as v1 / v2.
-// Used when the whole parent layer is resident; otherwise slos_tile_kernel (with its parent-window checks) runs.
-// ================================================================================================================
-#define LEAN_DB 128
-
-struct __align__(16) LeanDesc {
-    uint64_t cbase;
-    const char *tptr;   // byte address of the tail-parent block of this prefix
-    double pfact;
-    int nz, pad;
-};
-
-__device__ __forceinline__ double2 ldg16(const char *base, uint32_t off) { return __ldg((const double2 *)(base + off)); }
-
-template <int D, int MODE, bool RANGECHK>
-__global__ void __launch_bounds__(TILE_BLOCK, 2) slos_lean_kernel(const __grid_constant__ TileArgs a) {
-    extern __shared__ __align__(16) unsigned char tile_smem[];
-    const int m = a.m, p = a.p, maxnz = a.maxnz;
-    const int tid = threadIdx.x;
-    double2 *s_u = (double2 *)tile_smem;
-    LeanDesc *s_desc = (LeanDesc *)(s_u + m);
-    double2 *e_u = (double2 *)(s_desc + LEAN_DB);
-    uint64_t *e_ptr = (uint64_t *)(e_u + LEAN_DB * maxnz);
-    __shared__ double s_red[TILE_BLOCK / 32];
-    const uint64_t *__restrict__ bt = a.bt;
-    const uint64_t *__restrict__ dt = a.dt;
-
-    for (int i = tid; i < m; i += TILE_BLOCK) s_u[i] = a.U[(size_t)i * m + a.mk];
-    int ci = 0;
-    for (int c = 1; c < a.ncls; ++c)
-        if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
-    const int w = a.cls[ci].w, u = a.cls[ci].u;
-    const uint32_t S = a.cls[ci].S, G = a.cls[ci].G, nchunks = a.cls[ci].nchunks;
-    const uint64_t local = (uint64_t)blockIdx.x - a.cls[ci].item_begin;
-    const uint32_t chunk = (uint32_t)(local % nchunks);
-    const uint64_t range = local / nchunks;
-    const uint64_t rho_a = a.cls[ci].rho_lo + range * a.cls[ci].per_item;
-    uint64_t rho_b = rho_a + a.cls[ci].per_item;
-    if (rho_b > a.cls[ci].rho_lo + a.cls[ci].np) rho_b = a.cls[ci].rho_lo + a.cls[ci].np;
-    __syncthreads();
-
-    // ---- per-thread tail: un-rank t in FS(D, u) once; byte offsets and U byte offsets of the occupied tail modes
-    uint32_t g, t;
-    if (G > 1) { g = tid / S; t = tid - g * S; } else { g = 0; t = chunk * TILE_BLOCK + tid; }
-    const bool active = (g < G) && (t < S);
-    uint32_t toffb[D];            // 16 * local rank of (tau - e_mode) in FS(D, u-1); 0 for unused entries
-    uint32_t uoff[(D + 3) / 4];   // 16 * tail mode of entry c, one byte each
-    int cnt = 0;
-#pragma unroll
-    for (int c = 0; c < (D + 3) / 4; ++c) uoff[c] = 0;
-    double tfact = 1.0;
-#pragma unroll
-    for (int c = 0; c < D; ++c) toffb[c] = 0;
-    if (active) {
-        uint64_t rem = t;
-        uint32_t E = 0;
-        int Tprev = u;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            int T = 0;
-            if (i < D - 1) {
-                const uint64_t *row = bt + (D - 1 - i) * FOCK_TMAX;
-                T = Tprev;
-                while (__ldg(row + T) > rem) --T;
-                rem -= __ldg(row + T);
-            }
-            const int si = Tprev - T;
-            if (si > 0) {
-                const uint32_t off = (t - E) << 4;
-#pragma unroll
-                for (int c = 0; c < D; ++c)
-                    if (c == cnt) { toffb[c] = off; uoff[c / 4] |= (uint32_t)(i * 16) << (8 * (c % 4)); }
-                ++cnt;
-                tfact *= c_factorial(si);
-            }
-            if (i < D - 1 && T > 0) E += (uint32_t)__ldg(dt + (D - 1 - i) * FOCK_TMAX + T);
-            Tprev = T;
-        }
-    }
-    const int wcnt = __reduce_max_sync(0xffffffffu, cnt);
-    const char *__restrict__ parent_b = (const char *)a.parent;
-    const char *s_utb = (const char *)(s_u + p);
-    const uint32_t t16 = t << 4;
-    double local_sum = 0.0;
-
-    for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += LEAN_DB) {
-        const int nb = (int)((rho_b - rho0) < (uint64_t)LEAN_DB ? (rho_b - rho0) : (uint64_t)LEAN_DB);
-        __syncthreads();
-        if (tid < nb) {   // cooperative prefix descriptors: thread i un-ranks prefix rho0 + i of FS(p, w)
-            uint64_t rem = rho0 + tid;
-            int Tprev = w;
-            uint64_t base = 0, E = 0;
-            int nz = 0;
-            double pf = 1.0;
-            for (int i = 0; i < p; ++i) {
-                int T = 0;
-                if (i < p - 1) {
-                    const uint64_t *row = bt + (p - 1 - i) * FOCK_TMAX;
-                    T = Tprev;
-                    while (__ldg(row + T) > rem) --T;
-                    rem -= __ldg(row + T);
-                }
-                const int si = Tprev - T;
-                const int Tfull = T + u;
-                if (si > 0) {
-                    e_ptr[tid * maxnz + nz] = E;
-                    e_u[tid * maxnz + nz] = s_u[i];
-                    ++nz;
-                    pf *= c_factorial(si);
-                }
-                base += __ldg(bt + (m - 1 - i) * FOCK_TMAX + Tfull);
-                if (Tfull > 0) E += __ldg(dt + (m - 1 - i) * FOCK_TMAX + Tfull);
-                Tprev = T;
-            }
-            for (int e = 0; e < nz; ++e) e_ptr[tid * maxnz + e] = (uint64_t)(parent_b + ((base - e_ptr[tid * maxnz + e]) << 4));
-            LeanDesc td;
-            td.cbase = base;
-            td.tptr = parent_b + ((base - E) << 4);
-            td.pfact = pf;
-            td.nz = nz;
-            td.pad = 0;
-            s_desc[tid] = td;
-        }
-        __syncthreads();
-        if (!active) continue;
-        for (int i = (int)g; i < nb; i += (int)G) {
-            const LeanDesc td = s_desc[i];
-            const uint64_t r = td.cbase + t;
-            if (RANGECHK && (r < a.cbegin || r >= a.cend)) continue;
-            const uint64_t *ep = e_ptr + i * maxnz;
-            const double2 *pu = e_u + i * maxnz;
-            const int nz = td.nz;
-            // ---- every load of this child is issued before any arithmetic
-            double2 pv0, pv1, pv2, pv3, tv[8];
-            if (nz > 0) pv0 = ldg16((const char *)ep[0], t16);
-            if (nz > 1) pv1 = ldg16((const char *)ep[1], t16);
-            if (nz > 2) pv2 = ldg16((const char *)ep[2], t16);
-            if (nz > 3) pv3 = ldg16((const char *)ep[3], t16);
-#pragma unroll
-            for (int c = 0; c < 8 && c < D; ++c)
-                if (c < wcnt) tv[c] = ldg16(td.tptr, toffb[c]);
-            double2 acc = make_double2(0.0, 0.0);
-            if (nz > 0) acc = cfma(pu[0], pv0, acc);
-            if (nz > 1) acc = cfma(pu[1], pv1, acc);
-            if (nz > 2) acc = cfma(pu[2], pv2, acc);
-            if (nz > 3) acc = cfma(pu[3], pv3, acc);
-            for (int e = 4; e < nz; ++e) acc = cfma(pu[e], ldg16((const char *)ep[e], t16), acc);
-#pragma unroll
-            for (int c = 0; c < 8 && c < D; ++c)
-                if (c < cnt) acc = cfma(*(const double2 *)(s_utb + ((uoff[c / 4] >> (8 * (c % 4))) & 0xFFu)), tv[c], acc);
-            if (D > 8 && wcnt > 8) {
-#pragma unroll
-                for (int c = 8; c < D; ++c)
-                    if (c < wcnt) tv[c - 8] = ldg16(td.tptr, toffb[c]);
-#pragma unroll
-                for (int c = 8; c < D; ++c)
-                    if (c < cnt) acc = cfma(*(const double2 *)(s_utb + ((uoff[c / 4] >> (8 * (c % 4))) & 0xFFu)), tv[c - 8], acc);
-            }
-            if (MODE & 1) a.child[r - a.cbegin] = acc;
-            if (MODE & 2) {
-                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
-                __stcs(a.probs + (r - a.cbegin), pr);
-                local_sum += pr;
-            }
-        }
-    }
-    if ((MODE & 2) && a.sum) {
-        local_sum = warp_sum(local_sum);
-        if ((tid & 31) == 0) s_red[tid >> 5] = local_sum;
-        __syncthreads();
-        if (tid < 32) {
-            double v = tid < TILE_BLOCK / 32 ? s_red[tid] : 0.0;
-            v = warp_sum(v);
-            if (tid == 0) atomicAdd(a.sum, v);
-        }
-    }
-}
-
-// ================================================================================================================
-// Pipelined tile kernel (v2c): the same tiling and sweep as slos_tile_kernel, but every parent a thread needs for prefix
-// i+1 is copied global -> shared with cp.async (LDGSTS, 16 B per lane, no registers) while the thread multiplies the
-// parents of prefix i out of its own shared-memory slots.  A thread only ever reads slots it filled itself, so the
-// only synchronisation is cp.async.wait_group.  Slot budget: an occupied mode holds >= 1 photon, so a child never has
-// more than k parents: nslots = max over classes of min(p,w) + min(D,u) <= k.
-// ================================================================================================================
-#define PIPE_DB 32
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int D, int MODE, bool RANGECHK>
-__global__ void __launch_bounds__(TILE_BLOCK, 2) slos_pipe_kernel(const __grid_constant__ TileArgs a) {
-    extern __shared__ __align__(16) unsigned char tile_smem[];
-    const int m = a.m, p = a.p, maxnz = a.maxnz, nslots = a.nslots;
-    const int tid = threadIdx.x;
-    double2 *s_u = (double2 *)tile_smem;
-    TileDesc *s_desc = (TileDesc *)(s_u + m);
-    double2 *e_u = (double2 *)(s_desc + PIPE_DB);
-    uint64_t *e_pb = (uint64_t *)(e_u + PIPE_DB * maxnz);
-    double2 *slots = (double2 *)(e_pb + PIPE_DB * maxnz);   // [2][nslots][TILE_BLOCK]
-    __shared__ double s_red[TILE_BLOCK / 32];
-    const uint64_t *__restrict__ bt = a.bt;
-    const uint64_t *__restrict__ dt = a.dt;
-
-    for (int i = tid; i < m; i += TILE_BLOCK) s_u[i] = a.U[(size_t)i * m + a.mk];
-    int ci = 0;
-    for (int c = 1; c < a.ncls; ++c)
-        if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
-    const int w = a.cls[ci].w, u = a.cls[ci].u;
-    const uint32_t S = a.cls[ci].S, G = a.cls[ci].G, nchunks = a.cls[ci].nchunks;
-    const uint64_t local = (uint64_t)blockIdx.x - a.cls[ci].item_begin;
-    const uint32_t chunk = (uint32_t)(local % nchunks);
-    const uint64_t range = local / nchunks;
-    const uint64_t rho_a = a.cls[ci].rho_lo + range * a.cls[ci].per_item;
-    uint64_t rho_b = rho_a + a.cls[ci].per_item;
-    if (rho_b > a.cls[ci].rho_lo + a.cls[ci].np) rho_b = a.cls[ci].rho_lo + a.cls[ci].np;
-    const int nzs = p < w ? p : w;   // slots [0, nzs) hold prefix parents, [nzs, nzs + cnt) tail parents
-    __syncthreads();
-
-    // ---- per-thread tail: un-rank t in FS(D, u) once; keep (mode, parent offset) of the occupied tail modes, compacted
-    uint32_t g, t;
-    if (G > 1) { g = tid / S; t = tid - g * S; } else { g = 0; t = chunk * TILE_BLOCK + tid; }
-    const bool active = (g < G) && (t < S);
-    uint32_t toff[D];
-    uint32_t tmode[(D + 5) / 6];
-    int cnt = 0;
-#pragma unroll
-    for (int c = 0; c < (D + 5) / 6; ++c) tmode[c] = 0;
-    double tfact = 1.0;
-#pragma unroll
-    for (int c = 0; c < D; ++c) toff[c] = 0;
-    if (active) {
-        uint64_t rem = t;
-        uint32_t E = 0;
-        int Tprev = u;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            int T = 0;
-            if (i < D - 1) {
-                const uint64_t *row = bt + (D - 1 - i) * FOCK_TMAX;
-                T = Tprev;
-                while (__ldg(row + T) > rem) --T;
-                rem -= __ldg(row + T);
-            }
-            const int si = Tprev - T;
-            if (si > 0) {
-                const uint32_t off = t - E;
-#pragma unroll
-                for (int c = 0; c < D; ++c)
-                    if (c == cnt) { toff[c] = off; tmode[c / 6] |= (uint32_t)i << (5 * (c % 6)); }
-                ++cnt;
-                tfact *= c_factorial(si);
-            }
-            if (i < D - 1 && T > 0) E += (uint32_t)__ldg(dt + (D - 1 - i) * FOCK_TMAX + T);
-            Tprev = T;
-        }
-    }
-    const int wcnt = __reduce_max_sync(0xffffffffu, cnt);
-    const double2 *__restrict__ parent = a.parent - a.pbegin;
-    const double2 *__restrict__ parent_t = parent + t;
-    const double2 *s_ut = s_u + p;
-    double2 *myslot = slots + tid;
-    double local_sum = 0.0;
-
-    for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += PIPE_DB) {
-        const int nb = (int)((rho_b - rho0) < (uint64_t)PIPE_DB ? (rho_b - rho0) : (uint64_t)PIPE_DB);
-        __syncthreads();
-        if (tid < nb) {   // cooperative prefix descriptors: thread i un-ranks prefix rho0 + i of FS(p, w)
-            uint64_t rem = rho0 + tid;
-            int Tprev = w;
-            uint64_t base = 0, E = 0;
-            int nz = 0;
-            double pf = 1.0;
-            for (int i = 0; i < p; ++i) {
-                int T = 0;
-                if (i < p - 1) {
-                    const uint64_t *row = bt + (p - 1 - i) * FOCK_TMAX;
-                    T = Tprev;
-                    while (__ldg(row + T) > rem) --T;
-                    rem -= __ldg(row + T);
-                }
-                const int si = Tprev - T;
-                const int Tfull = T + u;
-                if (si > 0) {
-                    e_pb[tid * maxnz + nz] = E;
-                    e_u[tid * maxnz + nz] = s_u[i];
-                    ++nz;
-                    pf *= c_factorial(si);
-                }
-                base += __ldg(bt + (m - 1 - i) * FOCK_TMAX + Tfull);
-                if (Tfull > 0) E += __ldg(dt + (m - 1 - i) * FOCK_TMAX + Tfull);
-                Tprev = T;
-            }
-            for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
-            TileDesc td;
-            td.cbase = base;
-            td.tbase = base - E;
-            td.pfact = pf;
-            td.nz = nz;
-            td.pad = 0;
-            s_desc[tid] = td;
-        }
-        __syncthreads();
-        if (!active || (int)g >= nb) continue;
-
-        // issue the copies of prefix i into buffer b
-        auto issue = [&](int i, int b) {
-            const TileDesc td = s_desc[i];
-            if (RANGECHK) {
-                const uint64_t r = td.cbase + t;
-                if (r < a.cbegin || r >= a.cend) return;
-            }
-            double2 *dst = myslot + (size_t)b * nslots * TILE_BLOCK;
-            const uint64_t *pb = e_pb + i * maxnz;
-            for (int e = 0; e < td.nz; ++e) cp_async16(dst + e * TILE_BLOCK, parent_t + pb[e]);
-            const double2 *__restrict__ tbp = parent + td.tbase;
-            double2 *dt2 = dst + nzs * TILE_BLOCK;
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                if (c >= wcnt) break;
-                if (c < cnt) cp_async16(dt2 + c * TILE_BLOCK, tbp + toff[c]);
-            }
-        };
-        int i = (int)g, b = 0;
-        issue(i, 0);
-        cp_async_commit();
-        for (; i < nb; i += (int)G) {
-            const int in = i + (int)G;
-            if (in < nb) issue(in, b ^ 1);
-            cp_async_commit();
-            if (in < nb) cp_async_wait<1>();
-            else cp_async_wait<0>();
-            const TileDesc td = s_desc[i];
-            const uint64_t r = td.cbase + t;
-            if (!RANGECHK || (r >= a.cbegin && r < a.cend)) {
-                const double2 *src = myslot + (size_t)b * nslots * TILE_BLOCK;
-                const double2 *pu = e_u + i * maxnz;
-                // one accumulator, modes in ascending order: the same rounding sequence as the v1 / v2 kernels, so results
-                // are bit-identical whichever kernel (and whichever sharding) produced them
-                double2 acc = make_double2(0.0, 0.0);
-                for (int e = 0; e < td.nz; ++e) acc = cfma(pu[e], src[e * TILE_BLOCK], acc);
-                const double2 *st2 = src + nzs * TILE_BLOCK;
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    if (c >= wcnt) break;
-                    if (c < cnt) acc = cfma(s_ut[(tmode[c / 6] >> (5 * (c % 6))) & 31u], st2[c * TILE_BLOCK], acc);
-                }
-                if (MODE & 1) a.child[r - a.cbegin] = acc;
-                if (MODE & 2) {
-                    const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tfact);
-                    __stcs(a.probs + (r - a.cbegin), pr);
-                    local_sum += pr;
-                }
-            }
-            b ^= 1;
-        }
-    }
-    if ((MODE & 2) && a.sum) {
-        local_sum = warp_sum(local_sum);
-        if ((tid & 31) == 0) s_red[tid >> 5] = local_sum;
-        __syncthreads();
-        if (tid < 32) {
-            double v = tid < TILE_BLOCK / 32 ? s_red[tid] : 0.0;
-            v = warp_sum(v);
-            if (tid == 0) atomicAdd(a.sum, v);
-        }
-    }
-}
-
 // ---------------------------------------------------------------- host side
-bool slos_mu_supports(int D, int k);
 bool slos_thin_supports(int D, int k);           // slos_thin.cu
-int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st,
-                     bool hybrid);
+int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);                   // slos_mu.cu
-int slos_mu_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
-int slos_blk_tail_modes(int m);                 // slos_blk.cu
-int slos_blk_u_limit(fock_ctx *c, int D, int k);
-int slos_layer_blocks(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, double *d_child,
-                      double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb, uint64_t ce, cudaStream_t st);
 
 static int slos_check(const char *who, fock_ctx *c, int m, int k) {
     FOCK_REQUIRE(c != nullptr, FOCK_ERR_ARG, "%s: ctx is NULL", who);
@@ -886,37 +497,6 @@ static int slos_tail_modes(int m) {
 }
 
 template <int D>
-static int launch_lean(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, size_t smem, cudaStream_t st) {
-#define LEAN_LAUNCH(MODE, CHK)                                                                                              \
-    do {                                                                                                                  \
-        FOCK_CUDA(cudaFuncSetAttribute(slos_lean_kernel<D, MODE, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        slos_lean_kernel<D, MODE, CHK><<<grid, TILE_BLOCK, smem, st>>>(a);                                                \
-    } while (0)
-    if (want_probs && want_child) { if (rangechk) LEAN_LAUNCH(3, true); else LEAN_LAUNCH(3, false); }
-    else if (want_probs) { if (rangechk) LEAN_LAUNCH(2, true); else LEAN_LAUNCH(2, false); }
-    else { if (rangechk) LEAN_LAUNCH(1, true); else LEAN_LAUNCH(1, false); }
-#undef LEAN_LAUNCH
-    c->launches++;
-    return fock_check_cuda(cudaGetLastError(), "slos_lean_kernel");
-}
-
-template <int D>
-static int launch_pipe(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, size_t smem, cudaStream_t st) {
-#define PIPE_LAUNCH(MODE, CHK)                                                                                              \
-    do {                                                                                                                  \
-        FOCK_CUDA(cudaFuncSetAttribute(slos_pipe_kernel<D, MODE, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        FOCK_CUDA(cudaFuncSetAttribute(slos_pipe_kernel<D, MODE, CHK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   \
-        slos_pipe_kernel<D, MODE, CHK><<<grid, TILE_BLOCK, smem, st>>>(a);                                                \
-    } while (0)
-    if (want_probs && want_child) { if (rangechk) PIPE_LAUNCH(3, true); else PIPE_LAUNCH(3, false); }
-    else if (want_probs) { if (rangechk) PIPE_LAUNCH(2, true); else PIPE_LAUNCH(2, false); }
-    else { if (rangechk) PIPE_LAUNCH(1, true); else PIPE_LAUNCH(1, false); }
-#undef PIPE_LAUNCH
-    c->launches++;
-    return fock_check_cuda(cudaGetLastError(), "slos_pipe_kernel");
-}
-
-template <int D>
 static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_probs, int check, unsigned grid, size_t smem, cudaStream_t st) {
 #define TILE_LAUNCH(MODE, CHK)                                                                                              \
     do {                                                                                                                  \
@@ -940,10 +520,10 @@ static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
 
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
-                            uint64_t ce, cudaStream_t st, int u_from = 0, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
+                            uint64_t ce, cudaStream_t st, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
                             uint64_t gap_e = UINT64_MAX) {
-    // gfilter: 0 = every class, 1 = only classes whose tail block fills a CTA (S >= 256; v4 kernel, slos_mu.cu),
-    //          2 = only the small classes (S < 256; v2 kernel)
+    // gfilter: 0 = every class (tile kernel), 1 = only classes whose tail block fills a CTA (S >= 256) in the hybrid thin
+    //          kernel (slos_thin.cu), 2 = only the small classes (S < 256) in the tile kernel
     const int p = m - D;
     TileArgs a;
     memset(&a, 0, sizeof a);
@@ -968,13 +548,11 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     int ncls = 0;
     // classes with small tail blocks first: their CTAs walk many prefixes with little work each and would otherwise run
     // alone at the end of the grid
-    const int w_first = slos_env_int("FOCK_TILE_SMALL_FIRST", 1) ? k : 0, w_step = w_first ? -1 : 1;
-    for (int w = w_first; w >= 0 && w <= k; w += w_step) {
+    for (int w = k; w >= 0; --w) {
         const int u = k - w;
-        if (u < u_from) continue;   // classes below u_from are handled by the block-staged kernel (slos_blk.cu)
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
-        if (((gfilter == 1 || gfilter == 3 || gfilter == 4) && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
+        if ((gfilter == 1 && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
         uint64_t lo = 0, hi = np_total;
         if (!full) {
             // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
@@ -994,7 +572,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         tc.rho_lo = lo; tc.np = hi - lo;
         // prefixes per CTA: 128 sweep steps for full tiles (512: 21.0 ms, 128: 20.5 ms for the 12/24 chain -- mid-size layers need the CTAs); packed small tiles (G prefixes per step) get short items so that
         // they spread over many CTAs instead of one CTA walking tens of thousands of prefixes
-        tc.per_item = (uint64_t)(tc.G > 1 ? slos_env_int("FOCK_TILE_PERITEM_SMALL", 32) : slos_env_int("FOCK_TILE_PERITEM", 128)) * tc.G;
+        tc.per_item = (uint64_t)(tc.G > 1 ? 32 : 128) * tc.G;
         tc.item_begin = items;
         items += ((tc.np + tc.per_item - 1) / tc.per_item) * tc.nchunks;
     }
@@ -1003,60 +581,15 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     FOCK_REQUIRE(items < (1ull << 31), FOCK_ERR_LIMIT, "slos: too many work items");
     size_t smem = (size_t)2 * m * FOCK_TMAX * 8 + (size_t)m * 16 + 34 * 8 + (size_t)TILE_DB * sizeof(TileDesc) +
                   (size_t)TILE_DB * a.maxnz * 24 + 16;
-    {
-        static int fast_setup = -1;
-        if (fast_setup < 0) fast_setup = slos_env_int("FOCK_TILE_FAST_SETUP", 1);
-        if (fast_setup && D <= 16 && k <= 15) {   // cached occupation tuples (4 bits / tail mode): see slos_mu.cu
-            for (int i = 0; i < ncls; ++i)
-                if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
-            smem += (size_t)D * TILE_BLOCK * 8;
-        }
+    if (D <= 16 && k <= 15) {   // cached occupation tuples (4 bits / tail mode): see slos_mu.cu
+        for (int i = 0; i < ncls; ++i)
+            if (int rc = slos_mu_tuples(c, D, a.cls[i].u, a.cls[i].S, st, &a.tup[i])) return rc;
+        smem += (size_t)D * TILE_BLOCK * 8;
     }
     const bool parent_whole = pb == 0 && pe == fock_count(m, k - 1) && !gapped;
     const int check = !parent_whole ? 2 : (full ? 0 : 1);
     const bool wc = d_child != nullptr, wp = d_probs != nullptr;
-    if (gfilter == 1) return slos_mu_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
-    if (gfilter == 3 || gfilter == 4) return slos_thin_launch(c, D, a, wc, wp, !full, (unsigned)items, st, gfilter == 4);
-    // lean variant when the whole parent layer is resident (no parent-window checks needed)
-    {
-        static int use_lean = -1;
-        if (use_lean < 0) use_lean = slos_env_int("FOCK_TILE_LEAN", 0);   // measured 18.6 ms vs 16.0 ms (v2) for the last 12/24 layer
-        const size_t lsmem = (size_t)m * 16 + (size_t)LEAN_DB * sizeof(LeanDesc) + (size_t)LEAN_DB * a.maxnz * 24 + 16;
-        if (use_lean && parent_whole && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
-            switch (D) {
-                case 4: return launch_lean<4>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-                case 6: return launch_lean<6>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-                case 8: return launch_lean<8>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-                case 10: return launch_lean<10>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-                case 12: return launch_lean<12>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-                default: return launch_lean<16>(c, a, wc, wp, !full, (unsigned)items, lsmem, st);
-            }
-        }
-    }
-    // pipelined variant (cp.async double buffering) when the whole parent layer is resident and two CTAs fit an SM
-    {
-        int nslots = 1;
-        for (int i = 0; i < ncls; ++i) {
-            const int w = a.cls[i].w, u = a.cls[i].u;
-            const int ns = (p < w ? p : w) + (D < u ? D : u);
-            if (ns > nslots) nslots = ns;
-        }
-        a.nslots = nslots;
-        const size_t psmem = (size_t)m * 16 + (size_t)PIPE_DB * sizeof(TileDesc) + (size_t)PIPE_DB * a.maxnz * 24 +
-                             (size_t)2 * nslots * TILE_BLOCK * 16;
-        static int use_pipe = -1;
-        if (use_pipe < 0) use_pipe = slos_env_int("FOCK_TILE_PIPE", 0);   // measured slower than the register-staged kernels
-        if (use_pipe && parent_whole && psmem <= 113 * 1024 && D <= 16 && ((uintptr_t)d_parent & 15) == 0) {
-            switch (D) {
-                case 4: return launch_pipe<4>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-                case 6: return launch_pipe<6>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-                case 8: return launch_pipe<8>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-                case 10: return launch_pipe<10>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-                case 12: return launch_pipe<12>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-                default: return launch_pipe<16>(c, a, wc, wp, !full, (unsigned)items, psmem, st);
-            }
-        }
-    }
+    if (gfilter == 1) return slos_thin_launch(c, D, a, wc, wp, !full, (unsigned)items, st);
     switch (D) {
         case 4: return launch_tile<4>(c, a, wc, wp, check, (unsigned)items, smem, st);
         case 6: return launch_tile<6>(c, a, wc, wp, check, (unsigned)items, smem, st);
@@ -1081,47 +614,25 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     if (cb == ce) return FOCK_OK;
     ScopedDevice sd(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // large layers: block-staged kernel (v3, slos_blk.cu) when the whole parent layer is resident, else the tile kernel
-    // (v2); small layers / few modes: the per-child gather kernel (v1)
-    static int force = -1;
+    // Policy.  Small layers / few modes: per-child gather kernel.  Otherwise the prefix/tail tile kernel; large probability
+    // layers with at most 8 prefix modes and the whole parent resident run their full tiles in the hybrid thin kernel
+    // (slos_thin.cu: last 12/24 layer 12.2 ms vs 13.5 ms) and only their small classes in the tile kernel.
+    // FOCK_SLOS_KERNEL=gather|tile pins one kernel (parity tests run every kernel on the same inputs).
+    static int force = -1;   // 0 auto, 1 gather, 2 tile
     if (force < 0) {
         const char *e = getenv("FOCK_SLOS_KERNEL");
-        force = (e && !strcmp(e, "v1")) ? 1 : ((e && !strcmp(e, "v3")) ? 0 : 2);
+        force = (e && !strcmp(e, "gather")) ? 1 : ((e && !strcmp(e, "tile")) ? 2 : 0);
     }
     if (force != 1 && (ce - cb) >= 32768) {
-        const int Db = slos_blk_tail_modes(m);
         const bool gapped = gap_b < gap_e && gap_b < pe;
         const bool parent_full = (pb == 0 && pe == fock_count(m, k - 1)) && !gapped;
-        if (force == 0 && Db > 0 && parent_full && ((uintptr_t)d_parent & 15) == 0) {
-            const int u_lim = slos_blk_u_limit(c, Db, k);
-            FOCK_REQUIRE(u_lim > 0, FOCK_ERR_CUDA, "slos: could not build the tail tables");
-            if (int rc = slos_layer_blocks(c, Db, m, k, d_U, mk, d_parent, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st)) return rc;
-            if (u_lim <= k)
-                return slos_layer_tiles(c, Db, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, u_lim);
-            return FOCK_OK;
-        }
         const int D = slos_tail_modes(m);
-        static int use_mu = -1;
-        if (use_mu < 0) {
-            const char *e = getenv("FOCK_SLOS_KERNEL");
-            use_mu = (e && !strcmp(e, "v4")) ? 1 : ((e && !strcmp(e, "v5")) ? 2 : ((e && !strcmp(e, "v6")) ? 3 : ((e && !strcmp(e, "v2")) ? -2 : 0)));
+        const bool thin = force == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
+        if (D > 0 && thin && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1)) return rc;
+            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 2);
         }
-        // default policy: the hybrid thin kernel (v6, slos_thin.cu) for large probability layers with at most 8 prefix modes
-        // (measured: last 12/24 layer 12.2 ms vs 13.5 ms with v2; with more prefix rows per child -- 13/26 -- or on the smaller
-        // coefficient layers v2 is faster); FOCK_SLOS_KERNEL=v2 / v4 / v5 / v6 forces one kernel
-        const bool auto_v6 = use_mu == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
-        if (D > 0 && (use_mu == 2 || use_mu == 3 || auto_v6) && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
-            // v5 / v6 (slos_thin.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
-            const int gf = (use_mu == 2) ? 3 : 4;
-            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gf)) return rc;
-            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
-        }
-        if (D > 0 && use_mu == 1 && parent_full && slos_mu_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
-            // v4 (slos_mu.cu) for the classes whose tail block fills a CTA, v2 for the few small ones
-            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 1)) return rc;
-            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 2);
-        }
-        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, 0, gap_b, gap_e);
+        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gap_b, gap_e);
     }
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
@@ -1255,13 +766,10 @@ extern "C" int slos_prob_distribution(fock_ctx *c, int m, const double *d_U, con
     ScopedDevice sd(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_sum) FOCK_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), st));
-    const double one[2] = {1.0, 0.0};
-    if (n == 0) {
-        const double p1 = 1.0;
-        FOCK_CUDA(cudaMemcpyAsync(d_probs, &p1, sizeof(double), cudaMemcpyHostToDevice, st));
-        if (d_coefs) FOCK_CUDA(cudaMemcpyAsync(d_coefs, one, 16, cudaMemcpyHostToDevice, st));
-        if (d_sum) FOCK_CUDA(cudaMemcpyAsync(d_sum, &p1, sizeof(double), cudaMemcpyHostToDevice, st));
-        FOCK_CUDA(cudaStreamSynchronize(st));
+    if (n == 0) {   // one state (the vacuum), probability 1: device-to-device from the context's constant 1 + 0i
+        FOCK_CUDA(cudaMemcpyAsync(d_probs, c->d_vacuum, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (d_coefs) FOCK_CUDA(cudaMemcpyAsync(d_coefs, c->d_vacuum, 16, cudaMemcpyDeviceToDevice, st));
+        if (d_sum) FOCK_CUDA(cudaMemcpyAsync(d_sum, c->d_vacuum, sizeof(double), cudaMemcpyDeviceToDevice, st));
         return FOCK_OK;
     }
     int order[FOCK_NMAX];
@@ -1270,10 +778,7 @@ extern "C" int slos_prob_distribution(fock_ctx *c, int m, const double *d_U, con
     // layers alternate between the two workspaces so that layer n-1 lands in work_a
     FOCK_REQUIRE(n == 1 || d_work_a, FOCK_ERR_ARG, "slos_prob_distribution: d_work_a is NULL");
     FOCK_REQUIRE(n <= 2 || d_work_b, FOCK_ERR_ARG, "slos_prob_distribution: d_work_b is NULL");
-    // layer 0 = [1] lives in the scratch area of the context
-    double *layer0 = c->d_scratch + 8;
-    FOCK_CUDA(cudaMemcpyAsync(layer0, one, 16, cudaMemcpyHostToDevice, st));
-    const double *prev = layer0;
+    const double *prev = c->d_vacuum;   // layer 0 = [1]: read-only constant of the context (safe on any stream)
     for (int k = 1; k <= n; ++k) {
         const uint64_t np = fock_count(m, k - 1), nc = fock_count(m, k);
         if (k == n) {
@@ -1288,9 +793,7 @@ extern "C" int slos_prob_distribution(fock_ctx *c, int m, const double *d_U, con
             prev = cur;
         }
     }
-    // the 16-byte host source of layer0 must stay valid until the copy ran
-    FOCK_CUDA(cudaStreamSynchronize(st));
-    return FOCK_OK;
+    return FOCK_OK;   // asynchronous on `stream`
 }
 
 extern "C" int slos_prob_distribution_host(fock_ctx *c, int m, const double *h_U, const uint8_t *in_state, double *h_probs,

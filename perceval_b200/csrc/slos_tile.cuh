@@ -1,4 +1,4 @@
-// slos_tile.cuh -- work-plan structures shared by the SLOS tile kernels (slos.cu: v2 family, slos_mu.cu: v4).
+// slos_tile.cuh -- work-plan structures shared by the SLOS tile kernels (slos.cu: tile kernel, slos_thin.cu: hybrid thin kernel).
 #pragma once
 #include "common.cuh"
 
@@ -25,9 +25,9 @@ struct TileArgs {
     double inv_in_fact;
     uint64_t cbegin, cend;
     int *status;
-    int nslots;                // pipelined kernel: shared-memory slots per thread and buffer
+    int uslot;                 // thin kernel: which constant-bank copy of the unitary column this launch reads
     TileClass cls[FOCK_TMAX];
-    const uint64_t *tup[FOCK_TMAX];   // v4 kernel: per class, the occupation tuple (4 bits / tail mode) of every tail rank
+    const uint64_t *tup[FOCK_TMAX];   // per class, the occupation tuple (4 bits / tail mode) of every tail rank
 };
 
 struct __align__(16) TileDesc {

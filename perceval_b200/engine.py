@@ -103,18 +103,30 @@ class FockEngine:
         return out
 
     # ------------------------------------------------------------------ FSMask
-    def mask_flags(self, m: int, n: int, mask, begin: int = 0, end: int | None = None, allow_missing: bool = False) -> torch.Tensor:
-        """uint8 device tensor: 1 where state #(begin+i) of FSArray(m, n) matches ``mask`` (a masks.FockMask)."""
+    def mask_flags(self, m: int, n: int, mask, begin: int = 0, end: int | None = None, allow_missing=False,
+                   budget: int | None = None) -> torch.Tensor:
+        """uint8 device tensor: 1 where state #(begin+i) of FSArray(m, n) matches ``mask`` (a masks.FockMask).
+        ``allow_missing``: partial match of intermediate layers; with ``budget`` = b only the partial matches that b more
+        photons can still complete (C ABI fock_mask_match, allow_missing = 2 + b)."""
         end = self.count(m, n) if end is None else end
         conds = mask.conds_array()
         flags = torch.empty(end - begin, dtype=torch.uint8, device=self.device)
+        am = (2 + int(budget)) if budget is not None else (1 if allow_missing else 0)
         check(self.lib.fock_mask_match(self.ctx, m, n, conds.ctypes.data_as(C.c_void_p), conds.shape[0], mask.at_least_bits(),
-                                       1 if allow_missing else 0, begin, end, flags.data_ptr(), self._stream()), "fock_mask_match")
+                                       am, begin, end, flags.data_ptr(), self._stream()), "fock_mask_match")
         return flags
 
-    def mask_ranks(self, m: int, n: int, mask) -> torch.Tensor:
-        """Ranks (int64, ascending = FSArray order) of the states of FSArray(m, n) the mask keeps."""
-        return torch.nonzero(self.mask_flags(m, n, mask)).view(-1)
+    def mask_ranks(self, m: int, n: int, mask, budget: int | None = None, chunk: int = 1 << 28) -> torch.Tensor:
+        """Ranks (int64, ascending = FSArray order) of the states of FSArray(m, n) the mask keeps (exact match), or with
+        ``budget`` = b the states b more photons can still turn into a match (pruned SLOS layers).  The rank space is
+        scanned in chunks so that the temporary flags never exceed ``chunk`` bytes."""
+        N = self.count(m, n)
+        out = []
+        for lo in range(0, N, chunk):
+            hi = min(N, lo + chunk)
+            idx = torch.nonzero(self.mask_flags(m, n, mask, lo, hi, budget=budget)).view(-1)
+            out.append(idx + lo if lo else idx)
+        return torch.cat(out) if len(out) != 1 else out[0]
 
     # ------------------------------------------------------------------ SLOS
     def slos_order(self, state) -> list:
@@ -168,6 +180,23 @@ class FockEngine:
                                             probs.data_ptr(), psum.data_ptr() if psum is not None else None, float(in_prodnfact),
                                             child_begin, child_end, self._stream()), "slos_layer_probs_seg")
         return probs
+
+    def slos_layer_masked(self, m: int, k: int, U: torch.Tensor, mk: int, parent_ranks: torch.Tensor, parent: torch.Tensor,
+                          child_ranks: torch.Tensor, in_prodnfact: float = 1.0, want_coefs: bool = True, want_probs: bool = False,
+                          want_amps: bool = False, psum: torch.Tensor | None = None):
+        """One layer over a pruned rank space (C ABI slos_layer_masked): ``parent`` is packed in the order of the ascending
+        int64 ``parent_ranks``; returns (coefs|None, probs|None, amps|None) packed in the order of ``child_ranks``."""
+        nc = child_ranks.numel()
+        coefs = torch.empty(nc, dtype=torch.complex128, device=self.device) if want_coefs else None
+        probs = torch.empty(nc, dtype=torch.float64, device=self.device) if want_probs else None
+        amps = torch.empty(nc, dtype=torch.complex128, device=self.device) if want_amps else None
+        assert parent.numel() == parent_ranks.numel() and parent_ranks.dtype == torch.int64 and child_ranks.dtype == torch.int64
+        check(self.lib.slos_layer_masked(self.ctx, m, k, U.data_ptr(), mk, parent_ranks.data_ptr(), parent_ranks.numel(), parent.data_ptr(),
+                                         child_ranks.data_ptr(), nc, coefs.data_ptr() if want_coefs else None,
+                                         probs.data_ptr() if want_probs else None, amps.data_ptr() if want_amps else None,
+                                         psum.data_ptr() if psum is not None else None, float(in_prodnfact), self._stream()),
+              "slos_layer_masked")
+        return coefs, probs, amps
 
     def slos_probs_windowed(self, U: torch.Tensor, in_state, child_begin: int, child_end: int, probs: torch.Tensor | None = None,
                             psum: torch.Tensor | None = None, plan=None, buffers=None, last_events: list | None = None):

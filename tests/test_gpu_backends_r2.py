@@ -1,0 +1,194 @@
+"""GPU: round-2 backend features -- compute tree shared by several inputs (reference _slos.py:61-86,170-185,
+tests/backends/test_backends.py:145-157), pruned rank space under masks (_slos.py:156-166), host-buffer and lazy paths,
+output layer sharded over several devices of one process, sampler prefetch pool."""
+import numpy as np
+import pytest
+import torch
+
+import perceval_b200 as pb
+from perceval_b200 import BackendFactory, BasicState, UnitaryCircuit, fsarray
+from perceval_b200.masks import FockMask
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shared_path_three_noisy_inputs(oracle):
+    """3 inputs sharing 2 photons: the shared layers are computed once (4 layers instead of 8; launch count asserted)
+    and every input matches the oracle."""
+    m = 7
+    u = oracle.random_unitary(m, seed=9)
+    sts = [BasicState([1, 1, 1, 0, 0, 0, 0]), BasicState([1, 1, 0, 1, 0, 0, 0]), BasicState([1, 1, 0, 0, 0, 0, 0])]
+    b = BackendFactory.get_backend("SLOS_B200")
+    b.set_circuit(UnitaryCircuit(u))
+    eng = b._eng()
+    l0 = eng.launch_count()
+    assert b.preprocess(sts) is True
+    assert b.stats["layers_computed"] == 4
+    # 4 layer launches (small layers: one gather kernel each) + 3 probability epilogues
+    assert eng.launch_count() - l0 == 7
+    assert b.preprocess(sts) is False                       # nothing new: no work
+    assert eng.launch_count() - l0 == 7
+    for st in sts:
+        ref = oracle.slos_probs(u, tuple(st))
+        got = np.array(b.all_prob(st))
+        assert np.abs(got - ref).max() <= 1e-10 * ref.max()
+        amps = b.all_amplitudes_tensor().cpu().numpy()
+        assert np.abs(amps - oracle.slos_amplitudes(u, tuple(st))).max() < 1e-12
+    assert b.stats["layers_computed"] == 4                   # queries were served from the cache
+    # separate backends (one chain each) give the same numbers
+    for st in sts:
+        b1 = BackendFactory.get_backend("SLOS_B200")
+        b1.set_circuit(UnitaryCircuit(u))
+        assert np.abs(np.array(b1.all_prob(st)) - np.array(b.all_prob(st))).max() < 1e-14
+
+
+def test_shared_path_mixed_photon_numbers_and_bunching(oracle):
+    m = 6
+    u = oracle.random_unitary(m, seed=4)
+    sts = [BasicState(s) for s in ([2, 1, 0, 1, 0, 0], [2, 0, 0, 1, 0, 0], [0, 0, 0, 3, 1, 0], [2, 1, 0, 1, 0, 1], [0, 0, 0, 0, 0, 0])]
+    b = BackendFactory.get_backend("SLOS_B200")
+    b.set_circuit(UnitaryCircuit(u))
+    b.preprocess(sts)
+    separate = sum(s.n for s in sts)
+    assert b.stats["layers_computed"] < separate
+    for st in sts:
+        ref = oracle.slos_probs(u, tuple(st))
+        got = np.array(b.all_prob(st))
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-10 * ref.max()
+    # same-size circuit change: every deployed input is refreshed with the new unitary when next queried
+    u2 = oracle.random_unitary(m, seed=5)
+    b.set_circuit(UnitaryCircuit(u2))
+    for st in sts[:3]:
+        ref = oracle.slos_probs(u2, tuple(st))
+        assert np.abs(np.array(b.all_prob(st)) - ref).max() <= 1e-10 * ref.max()
+
+
+@pytest.mark.parametrize("m,st,masks,at_least", [
+    (8, (1, 1, 0, 1, 0, 1, 0, 0), ["******00"], None),
+    (8, (1, 1, 0, 1, 0, 1, 0, 0), ["*0****1*", "2*******"], None),
+    (6, (1, 0, 1, 0, 1, 0), ["1****0"], [0]),
+    (10, (1, 1, 1, 1, 1, 0, 0, 0, 0, 0), ["*****01010"], None),
+])
+def test_masked_run_is_pruned_and_equals_filtered_full_run(oracle, m, st, masks, at_least):
+    """With a mask every layer lives on the pruned rank space: fewer states stored and computed per layer, and the kept
+    probabilities / amplitudes equal the unmasked run filtered by the mask (not renormalised)."""
+    n = sum(st)
+    u = oracle.random_unitary(m, seed=13)
+    ref_p, ref_a = oracle.slos_probs(u, st), oracle.slos_amplitudes(u, st)
+    states = fsarray.enumerate_states(m, n)
+    keep = FockMask(m, n, [s.replace("*", " ") for s in masks], at_least).match_array(states)
+    b = BackendFactory.get_backend("SLOS_B200")
+    b.set_mask(masks, at_least_modes=at_least)
+    b.set_circuit(UnitaryCircuit(u))
+    b.set_input_state(BasicState(list(st)))
+    got = np.array(b.all_prob())
+    assert got.shape[0] == keep.sum()
+    assert np.abs(got - ref_p[keep]).max() <= 1e-10 * max(ref_p.max(), 1e-300)
+    amps = b.all_amplitudes_tensor().cpu().numpy()
+    assert np.abs(amps - ref_a[keep]).max() < 1e-12
+    for s_, p in zip(states[keep][:5], got[:5]):
+        assert abs(b.probability(BasicState([int(x) for x in s_])) - p) < 1e-13
+    # pruning: every intermediate layer holds fewer states than the full layer, and the kept sets are nested correctly
+    kept_sizes = {k: v.numel() for (k, budget), v in b._kept.items() if budget is not None}
+    assert kept_sizes and all(kept_sizes[k] < fsarray.count(m, k) for k in kept_sizes if k >= 2)
+    res = b._results[b._input_state]
+    assert res.coefs.numel() == keep.sum() and res.ranks.numel() == keep.sum()
+
+
+def test_masked_10_photons_22_modes_saves_memory_and_time(oracle):
+    """'****...00'-style herald mask at 10 photons / 22 modes, six heralded modes: the pruned run stores proportionally
+    fewer amplitudes and is faster than the full run, with identical kept probabilities."""
+    m, n = 22, 10
+    st = (1,) * n + (0,) * (m - n)
+    mask = "*" * 16 + "010100"
+    u = oracle.random_unitary(m, seed=2)
+    full = BackendFactory.get_backend("SLOS_B200")
+    full.set_circuit(UnitaryCircuit(u))
+    pf = full.all_prob_tensor(BasicState(list(st)))
+    b = BackendFactory.get_backend("SLOS_B200")
+    b.set_mask(mask)
+    b.set_circuit(UnitaryCircuit(u))
+    pm = b.all_prob_tensor(BasicState(list(st)))
+    ranks = b._results[b._input_state].ranks
+    assert pm.numel() == ranks.numel() < pf.numel() // 20
+    assert torch.allclose(pm, pf[ranks], rtol=0, atol=1e-10 * float(pf.max()))
+    stored = sum(v.numel() for (k, budget), v in b._kept.items() if budget is not None)
+    assert stored < sum(fsarray.count(m, k) for k in range(1, n + 1)) // 4
+
+    def timed(bk):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in (3, 4, 5):
+            bk.set_circuit(UnitaryCircuit(oracle.random_unitary(m, seed=s)))
+            bk.all_prob_tensor(BasicState(list(st)))
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+    timed(b), timed(full)
+    assert timed(b) < timed(full)
+
+
+def test_all_prob_into_host_buffer_lazy_and_cached(oracle):
+    m, st = 16, (1,) * 7 + (0,) * 9
+    u = oracle.random_unitary(m, seed=6)
+    ref = oracle.slos_probs(u, st)
+    host = torch.empty(ref.shape[0], dtype=torch.float64).pin_memory()
+    # lazy: the chain runs inside all_prob_into, last layer pipelined with the copies
+    b = pb.SLOSB200Backend(lazy_above=1000, max_cached_bytes=1 << 10)
+    b.set_circuit(UnitaryCircuit(torch.from_numpy(u).pin_memory()))
+    b.set_input_state(BasicState(list(st)))
+    assert b._input_state not in b._results
+    total = b.all_prob_into(host, pieces=5)
+    assert abs(total - 1.0) < 1e-12 and np.abs(host.numpy() - ref).max() <= 1e-10 * ref.max()
+    # eager + cached: plain copy of the cached distribution
+    b2 = BackendFactory.get_backend("SLOS_B200")
+    b2.set_circuit(UnitaryCircuit(u))
+    b2.set_input_state(BasicState(list(st)))
+    assert b2._input_state in b2._results
+    host.zero_()
+    total = b2.all_prob_into(host)
+    assert abs(total - 1.0) < 1e-12 and np.abs(host.numpy() - ref).max() <= 1e-10 * ref.max()
+    # a device-resident unitary is taken as it is
+    b3 = BackendFactory.get_backend("SLOS_B200")
+    b3.set_circuit(UnitaryCircuit(torch.from_numpy(u).cuda()))
+    assert np.abs(np.array(b3.all_prob(BasicState(list(st)))) - ref).max() <= 1e-10 * ref.max()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_device_ids_shards_output_layer(oracle):
+    m, st = 16, (1,) * 8 + (0,) * 8
+    u = oracle.random_unitary(m, seed=8)
+    ref = oracle.slos_probs(u, st)
+    ids = list(range(min(torch.cuda.device_count(), 4)))
+    b = pb.SLOSB200Backend(device_ids=ids)
+    b.set_circuit(UnitaryCircuit(u))
+    b.set_input_state(BasicState(list(st)))
+    shards = b.all_prob_shards()
+    assert len(shards) == len(ids) and {d.index for d, _, _ in shards} == set(ids)
+    for dev, (lo, hi), t in shards:
+        assert np.abs(t.cpu().numpy() - ref[lo:hi]).max() <= 1e-10 * ref.max()
+    assert np.abs(b.all_prob_tensor().cpu().numpy() - ref).max() <= 1e-10 * ref.max()
+    host = torch.empty(ref.shape[0], dtype=torch.float64).pin_memory()
+    assert abs(b.all_prob_into(host) - 1.0) < 1e-12 and np.abs(host.numpy() - ref).max() <= 1e-10 * ref.max()
+
+
+def test_sampler_prefetch_pool_is_bit_identical(oracle):
+    """Perceval asks for <= 1000 samples per call (noisy_sampling_simulator.py:232): with prefetch the backend launches
+    once per 8192 samples and hands out exactly the samples the un-pooled backend draws."""
+    m, st = 12, (1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0)
+    u = oracle.random_unitary(m, seed=1)
+    plain = pb.Clifford2017B200Backend(seed=77)
+    pooled = pb.Clifford2017B200Backend(seed=77, prefetch=8192)
+    for b in (plain, pooled):
+        b.set_circuit(UnitaryCircuit(u))
+        b.set_input_state(BasicState(list(st)))
+    l0 = pooled._eng().launch_count()
+    a = torch.cat([plain.samples_tensor(c) for c in (1000, 1000, 37, 9000, 1000, 1)])
+    l1 = pooled._eng().launch_count()
+    p = torch.cat([pooled.samples_tensor(c) for c in (1000, 1000, 37, 9000, 1000, 1)])
+    l2 = pooled._eng().launch_count()
+    assert torch.equal(a, p)
+    assert (l2 - l1) < (l1 - l0)
+    ref = oracle.cc2017_samples(u, st, 64, seed=77)
+    assert (a[:64].cpu().numpy() == ref).all()

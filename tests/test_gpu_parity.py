@@ -294,7 +294,7 @@ def test_slos_probs_to_host_pipelined(eng, oracle):
     eng.check_status()
 
 
-# ---------------------------------------------------------------- experimental SLOS kernels (selected by environment variable)
+# ---------------------------------------------------------------- every SLOS kernel of the policy, pinned by environment variable
 
 _VARIANT_SCRIPT = r"""
 import sys, numpy as np, torch
@@ -315,12 +315,11 @@ print("WORST", worst)
 """
 
 
-@pytest.mark.parametrize("env", [{"FOCK_SLOS_KERNEL": "v1"}, {"FOCK_SLOS_KERNEL": "v3"}, {"FOCK_TILE_PIPE": "1"},
-                                 {"FOCK_TILE_LEAN": "1"}, {"FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v4"},
-                                 {"FOCK_SLOS_KERNEL": "v4", "FOCK_SLOS_TAIL": "8"}, {"FOCK_SLOS_KERNEL": "v5"}, {"FOCK_SLOS_KERNEL": "v6"}, {"FOCK_SLOS_KERNEL": "v2"}])
+@pytest.mark.parametrize("env", [{"FOCK_SLOS_KERNEL": "gather"}, {"FOCK_SLOS_KERNEL": "tile"}, {"FOCK_SLOS_TAIL": "8"},
+                                 {"FOCK_SLOS_TAIL": "12"}, {"FOCK_SLOS_KERNEL": "tile", "FOCK_SLOS_TAIL": "6"}])
 def test_slos_kernel_variants_vs_oracle(env):
-    # every kernel variant profiles/README.md quotes is held to the same 1e-10 bar as the default (the variant is chosen
-    # once per process, hence the subprocess)
+    # the gather kernel, the tile kernel and the other tail widths of the policy are held to the same 1e-10 bar on the same
+    # inputs as the default (the choice is made once per process, hence the subprocess)
     import os
     import subprocess
     import sys
@@ -408,4 +407,100 @@ def test_large_probability_layer_default_kernel_sharded(eng, oracle):
     for b, e in zip(cuts[:-1], cuts[1:]):
         part = eng.slos_layer_probs(m, n, U, order[n - 1], parent, prodnfact(st), child_begin=b, child_end=e)
         assert torch.equal(part, full[b:e])
+    eng.check_status()
+
+
+# ---------------------------------------------------------------- BASELINE sizes: Glynn n = 25 .. 32, C&C 20 photons / 400 modes
+
+@pytest.mark.parametrize("n,frac", [(25, 1), (28, 1), (30, 1), (31, 2), (32, 4)])
+def test_glynn_big_kernel_headline_sizes_vs_oracle(eng, oracle, n, frac):
+    """glynn_big_kernel<n> at the sizes BASELINE.json names (reference perceval/backends/_naive.py:70-71): one Haar
+    sub-matrix per n.  n <= 30: the whole permanent against the oracle (8 s of OpenMP at n = 30); n >= 31: 1/frac of the Gray range, taken as three
+    sub-ranges (start, an unaligned middle piece, the end), each against the oracle's partial sum over the same codes,
+    plus the whole permanent against the sum of the device's own quarters (additivity over the Gray range)."""
+    u = oracle.random_unitary(2 * n, seed=n)
+    mat = np.ascontiguousarray(u[:n, :n])
+    M = torch.from_numpy(mat[None])
+    G = 1 << (n - 1)
+    if frac == 1:
+        got = complex(eng.permanents(M).cpu().numpy()[0])
+        ref = oracle.permanent(mat)
+        assert abs(got - ref) <= REL * abs(ref), (n, got, ref)
+        return
+    piece = G // (3 * frac)
+    scale = 0.0
+    for g0 in (0, G // 2 - piece // 2 + 12345, G - piece):
+        got = complex(eng.permanents(M, g0, g0 + piece).cpu().numpy()[0])
+        ref = oracle.permanent(mat, g0, g0 + piece)
+        scale = max(scale, abs(ref))
+        assert abs(got - ref) <= REL * abs(ref), (n, g0, got, ref)
+    whole = complex(eng.permanents(M).cpu().numpy()[0])
+    quarters = sum(complex(eng.permanents(M, q * (G // 4), (q + 1) * (G // 4)).cpu().numpy()[0]) for q in range(4))
+    assert abs(whole - quarters) <= 1e-9 * max(abs(whole), scale)
+
+
+def test_cc2017_20_photons_400_modes_bit_exact(eng, oracle):
+    """BASELINE config 4 (reference perceval/backends/_clifford2017.py:47-57 at 20 photons / 400 modes): the H = 5 kernel
+    template with its m = 400 shared-memory sizing, 64 samples bit for bit against the oracle's Philox stream."""
+    m, n, count = 400, 20, 64
+    st = (1,) * n + (0,) * (m - n)
+    u = oracle.random_unitary(m, seed=0)
+    U = eng.unitary(u)
+    got = eng.cc2017_samples(U, st, count, seed=99, offset=5).cpu().numpy()
+    ref = oracle.cc2017_samples(u, st, count, seed=99, offset=5)
+    assert (got.sum(axis=1) == n).all()
+    assert (got == ref).all(), int((got != ref).any(axis=1).sum())
+    # same stream for any batch split
+    a = eng.cc2017_samples(U, st, 24, seed=99, offset=5).cpu().numpy()
+    b = eng.cc2017_samples(U, st, 40, seed=99, offset=29).cpu().numpy()
+    assert (np.concatenate([a, b]) == got).all()
+
+
+def test_two_streams_one_device_run_concurrently_and_agree(eng, oracle):
+    """Two chains on two CUDA streams of one device (no shared mutable state in the library: per-launch constant-bank
+    copy of the unitary column, stream-ordered scratch): both match the single-stream result bit for bit, for SLOS
+    (thin + tile kernels), permanents and C&C samples."""
+    m, n = 24, 9   # 28 048 800 states: the probability layer runs the tile kernel; see the 22/11 test for the thin kernel
+    st = (1,) * n + (0,) * (m - n)
+    U1 = eng.unitary(oracle.random_unitary(m, seed=1))
+    U2 = eng.unitary(oracle.random_unitary(m, seed=2))
+    ref1, _, _ = eng.slos_probs(U1, st)
+    ref2, _, _ = eng.slos_probs(U2, st)
+    mats = torch.from_numpy(np.stack([oracle.random_unitary(36, seed=s)[:18, :18] for s in range(4)])).cuda()
+    perm_ref = eng.permanents(mats)
+    smp_ref = eng.cc2017_samples(U1, st, 256, seed=4)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            p1, _, _ = eng.slos_probs(U1, st)
+            pm1 = eng.permanents(mats)
+            sm1 = eng.cc2017_samples(U1, st, 256, seed=4)
+        with torch.cuda.stream(s2):
+            p2, _, _ = eng.slos_probs(U2, st)
+            pm2 = eng.permanents(mats)
+            sm2 = eng.cc2017_samples(U1, st, 256, seed=4)
+        torch.cuda.synchronize()
+        assert torch.equal(p1, ref1) and torch.equal(p2, ref2)
+        assert torch.equal(pm1, perm_ref) and torch.equal(pm2, perm_ref)
+        assert torch.equal(sm1, smp_ref) and torch.equal(sm2, smp_ref)
+    eng.check_status()
+
+
+def test_two_streams_thin_kernel(eng, oracle):
+    """Same, through the hybrid thin kernel (22 modes / 11 photons probability layer, >= 2^25 children)."""
+    from perceval_b200.engine import prodnfact
+    m, n = 22, 11
+    st = (1,) * n + (0,) * (m - n)
+    Us = [eng.unitary(oracle.random_unitary(m, seed=s)) for s in (3, 4)]
+    refs = [eng.slos_probs(U, st)[0] for U in Us]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for U, s_ in zip(Us, streams):
+        with torch.cuda.stream(s_):
+            outs.append(eng.slos_probs(U, st)[0])
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
     eng.check_status()
