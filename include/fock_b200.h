@@ -146,6 +146,10 @@ int cc2017_samples_host(fock_ctx *ctx, int m, int n, const double *h_U, const ui
 /* ---- measurement helpers (bench.py only) ------------------------------------------------------------------- */
 /* kind 0: FP64 FMA peak (returns TFLOP/s), 1: HBM stream read+write copy GB/s, 2: L2-resident read GB/s */
 int fock_measure_peak(fock_ctx *ctx, int kind, double *out_value);
+/* cudaEvent_t pair (as void*) recorded on the launching stream immediately before / after every probability-layer launch
+ * (slos_layer_probs, slos_layer_probs_seg, the last layer of slos_prob_distribution) until reset with (NULL, NULL): lets
+ * a caller time the dominant kernel inside a whole-chain call with CUDA events, without a profiler */
+int fock_profile_events(fock_ctx *ctx, void *ev_begin, void *ev_end);
 /* number of kernel launches issued through this context since creation */
 uint64_t fock_launch_count(fock_ctx *ctx);
 

@@ -46,6 +46,7 @@ SYMBOLS = [
     ("cc2017_samples", _i32, [_vp, _i32, _i32, _vp, _vp, _u64, _u64, _u64, _vp, _vp]),
     ("cc2017_samples_host", _i32, [_vp, _i32, _i32, _vp, _vp, _u64, _u64, _u64, _vp]),
     ("fock_measure_peak", _i32, [_vp, _i32, C.POINTER(_dbl)]),
+    ("fock_profile_events", _i32, [_vp, _vp, _vp]),
     ("fock_launch_count", _u64, [_vp]),
 ]
 

@@ -95,6 +95,7 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     c->total_mem = prop.totalGlobalMem;
     c->launches = 0;
     c->mu_state = nullptr;
+    c->ev_begin = c->ev_end = nullptr;
     slos_mu_init(c);
     {   // keep stream-ordered scratch (StreamScratch) in the pool between calls
         cudaMemPool_t pool;
@@ -157,6 +158,14 @@ extern "C" int fock_check_status(fock_ctx *c, void *stream) {
 }
 
 extern "C" uint64_t fock_launch_count(fock_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int fock_profile_events(fock_ctx *c, void *ev_begin, void *ev_end) {
+    FOCK_REQUIRE(c != nullptr, FOCK_ERR_ARG, "fock_profile_events: ctx is NULL");
+    FOCK_REQUIRE((ev_begin == nullptr) == (ev_end == nullptr), FOCK_ERR_ARG, "fock_profile_events: pass two events or two NULLs");
+    c->ev_begin = (cudaEvent_t)ev_begin;
+    c->ev_end = (cudaEvent_t)ev_end;
+    return FOCK_OK;
+}
 
 // ---------------------------------------------------------------- host rank / unrank (any m <= 64, n <= 32)
 static int check_mn(const char *who, int m, int n) {

@@ -614,6 +614,13 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
     if (cb == ce) return FOCK_OK;
     ScopedDevice sd(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    // measurement hook (bench.py roofline): CUDA events of the caller around the probability-layer launches, on their stream
+    struct EventBracket {
+        cudaEvent_t e;
+        cudaStream_t s;
+        EventBracket(cudaEvent_t b, cudaEvent_t e_, cudaStream_t s_) : e(e_), s(s_) { if (b) cudaEventRecord(b, s_); }
+        ~EventBracket() { if (e) cudaEventRecord(e, s); }
+    } bracket(d_probs ? c->ev_begin : nullptr, d_probs ? c->ev_end : nullptr, st);
     // Policy.  Small layers / few modes: per-child gather kernel.  Otherwise the prefix/tail tile kernel; large probability
     // layers with at most 8 prefix modes and the whole parent resident run their full tiles in the hybrid thin kernel
     // (slos_thin.cu: last 12/24 layer 12.2 ms vs 13.5 ms) and only their small classes in the tile kernel.

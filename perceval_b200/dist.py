@@ -239,6 +239,303 @@ def engine_slos_probs_windowed(engine, U, in_state, group=None, sub: int | None 
     return WindowedChain(engine, in_state, group, sub).run(U)
 
 
+def _intersect(segs, b: int, e: int):
+    """parts of the half-open ranges ``segs`` inside [b, e), merged"""
+    out = []
+    for lo, hi in segs:
+        lo, hi = max(lo, b), min(hi, e)
+        if hi > lo:
+            if out and lo <= out[-1][1]:
+                out[-1] = (out[-1][0], max(out[-1][1], hi))
+            else:
+                out.append((lo, hi))
+    return out
+
+
+def split_range(b: int, e: int, pieces: int):
+    pieces = max(1, min(pieces, e - b)) if e > b else 1
+    return [(b + (e - b) * i // pieces, b + (e - b) * (i + 1) // pieces) for i in range(pieces)]
+
+
+class ExchangePlan:
+    """Host-side plan of the owner-computes + halo-exchange partition of a SLOS chain.
+
+    Layers below ``k0`` are replicated (they are small: recomputing them costs less than one message); every layer
+    k >= k0 is cut in ``world`` contiguous rank ranges, rank q OWNS range q of every such layer and computes only that.
+    The parents of layer k-1 that the children [b, e) need are one or two contiguous rank ranges (partition.parent_segments,
+    exact), so what rank r must receive from rank q is a short list of slices of q's own range -- no whole-layer all-gather,
+    no recompute.  The own range of a rank is cut in ``pieces`` child pieces, computed in order; the exchange that follows a
+    layer is cut in the same number of GROUPS, group g carrying exactly the parents that child piece g of the next layer
+    needs and no earlier group carried.  Child piece g therefore starts as soon as group g has arrived, while groups g+1..
+    are still on the wire: the NVLink transfers of a layer overlap the computation of the next one.  Everything is integer
+    arithmetic, identical on every rank.
+    """
+
+    def __init__(self, m: int, n: int, world: int, pieces: int = 4, shard_min: int = 1 << 23, max_segments: int = 4,
+                 fractions=None):
+        from . import partition as P
+        self.m, self.n, self.world, self.pieces = m, n, world, pieces
+        cnt = [P.count(m, k) for k in range(n + 1)]
+        self.count = cnt
+        k0 = n
+        for k in range(1, n + 1):
+            if cnt[k] >= shard_min:
+                k0 = k
+                break
+        self.k0 = max(1, min(k0, n))
+        if fractions is None:
+            fractions = balanced_fractions(m, n, world)
+        self.fractions = fractions
+        self.own = {}      # k -> [(b, e)] per rank
+        self.piece = {}    # k -> per rank, [(b, e)] per piece
+        for k in range(self.k0, n + 1):
+            if fractions is not None:
+                bd = [0] + [min(cnt[k], max(0, int(round(f * cnt[k])))) for f in fractions[1:-1]] + [cnt[k]]
+                for q in range(1, len(bd)):
+                    bd[q] = max(bd[q], bd[q - 1])
+                self.own[k] = [(bd[q], bd[q + 1]) for q in range(world)]
+            else:
+                self.own[k] = [shard_range(cnt[k], q, world) for q in range(world)]
+            self.piece[k] = [split_range(b, e, pieces) for b, e in self.own[k]]
+        # need[k][q][j]: parent (layer k-1) segments of child piece j of rank q; fresh[k][q][j]: the part no earlier piece needs
+        self.need, self.fresh = {}, {}
+        for k in range(self.k0 + 1, n + 1):
+            self.need[k] = [[P.parent_segments(m, k, [pc], max_segments) if pc[1] > pc[0] else [] for pc in self.piece[k][q]]
+                            for q in range(world)]
+            self.fresh[k] = []
+            for q in range(world):
+                seen, out = [], []
+                for segs in self.need[k][q]:
+                    out.append(_subtract(segs, seen))
+                    seen = P.merge_segments(seen + list(segs), max_segments=1 << 30)
+                self.fresh[k].append(out)
+
+    def npieces(self, k: int, q: int) -> int:
+        return len(self.piece[k][q])
+
+    def groups(self, k: int) -> int:
+        """number of exchange groups after layer k (k0 <= k < n) = the largest child piece count of layer k+1"""
+        return max(len(p) for p in self.piece[k + 1])
+
+    def transfers(self, k: int, g: int, src: int, dst: int):
+        """slices of layer k (k0 <= k < n) that rank ``src`` sends to ``dst`` in group g: the part of src's own range that
+        child piece g of dst at layer k+1 needs and no earlier piece of dst needed"""
+        if src == dst or g >= len(self.fresh[k + 1][dst]):
+            return []
+        b, e = self.own[k][src]
+        return _intersect(self.fresh[k + 1][dst][g], b, e)
+
+    def recv_elems(self, r: int, k: int | None = None) -> int:
+        """complex elements rank r receives per step (after layer k only, if given)"""
+        tot = 0
+        for kk in ([k] if k is not None else range(self.k0, self.n)):
+            for g in range(self.groups(kk)):
+                for q in range(self.world):
+                    tot += sum(hi - lo for lo, hi in self.transfers(kk, g, q, r))
+        return tot
+
+    def send_elems(self, r: int, k: int | None = None) -> int:
+        tot = 0
+        for kk in ([k] if k is not None else range(self.k0, self.n)):
+            for g in range(self.groups(kk)):
+                for q in range(self.world):
+                    tot += sum(hi - lo for lo, hi in self.transfers(kk, g, r, q))
+        return tot
+
+    def model_ms(self, ps_per_state=None, nvlink_gbs: float = 600.0) -> float:
+        """modelled step time (ms): per layer, every rank computes its pieces as their groups arrive; a group takes the time of
+        its busiest rank (max of bytes sent and received) at ``nvlink_gbs``.  ps_per_state: {k: picoseconds per child}."""
+        n, W = self.n, self.world
+        ps = ps_per_state or {}
+        t_all = 0.0
+        arrive = None
+        for k in range(self.k0, n + 1):
+            cost = ps.get(k, 14.6 if k == n else 15.9) * 1e-9      # ms per child state
+            finish = []
+            for r in range(W):
+                t = 0.0
+                for j, (b, e) in enumerate(self.piece[k][r]):
+                    if arrive is not None and j < len(arrive):
+                        t = max(t, arrive[j])
+                    t += (e - b) * cost
+                finish.append(t)
+            t_layer = max(finish)
+            t_all += t_layer
+            if k < n:
+                arrive, t = [], 0.0
+                for g in range(self.groups(k)):
+                    worst = 0
+                    for r in range(W):
+                        rx = sum(hi - lo for q in range(W) for lo, hi in self.transfers(k, g, q, r))
+                        tx = sum(hi - lo for q in range(W) for lo, hi in self.transfers(k, g, r, q))
+                        worst = max(worst, rx, tx)
+                    t += 16.0 * worst / (nvlink_gbs * 1e6)
+                    arrive.append(t)
+        return t_all
+
+
+def _subtract(segs, seen):
+    """parts of ``segs`` not covered by the sorted, merged ranges ``seen``"""
+    out = []
+    for lo, hi in segs:
+        cur = lo
+        for a, b in seen:
+            if b <= cur:
+                continue
+            if a >= hi:
+                break
+            if a > cur:
+                out.append((cur, a))
+            cur = max(cur, b)
+            if cur >= hi:
+                break
+        if cur < hi:
+            out.append((cur, hi))
+    return out
+
+
+# Rank-space fractions of the own ranges, tuned offline with ExchangePlan.model_ms (tools_balance_exchange.py): ranks early
+# in FSArray order read parents spread over most of the previous layer and late ranks are read by everybody, so equal
+# counts leave the NVLink traffic 20x apart between ranks.  {(m, n, world): [0, f1, ..., 1]}; anything else: equal counts.
+BALANCED_FRACTIONS: dict = {}
+
+
+def balanced_fractions(m: int, n: int, world: int):
+    return BALANCED_FRACTIONS.get((m, n, world))
+
+
+class ExchangeChain:
+    """One SLOS chain under ExchangePlan on this rank.  The compute step is injected so that the exchange logic runs on CPU
+    with gloo in the tests:
+
+      layer_fn(k, mk, parent_full, out, b, e)        writes child ranks [b, e) of layer k into ``out`` (length e - b);
+                                                      parent_full is indexed by absolute rank (None: the vacuum, k = 1)
+      last_fn(k, mk, parent_full, out, psum, b, e)   same for the output layer: float64 probabilities + partial sum
+
+    Layers live in two full-size ping-pong buffers indexed by absolute rank (at 12 photons / 24 modes: 4.6 + 1.5 GB), so the
+    kernels run their whole-parent fast paths; only the ranks a rank owns or receives are ever written or read.
+    """
+
+    def __init__(self, m: int, in_state, order, plan: ExchangePlan, alloc, layer_fn, last_fn, group=None, alloc_real=None):
+        self.m = m
+        self.occ = [int(x) for x in in_state]
+        self.n = sum(self.occ)
+        assert self.n >= 1 and plan.n == self.n and plan.m == m
+        self.order = order
+        self.plan = plan
+        self.group = group
+        self.rank, self.world = _world(group)
+        assert self.world == plan.world, "plan built for another world size"
+        self.layer_fn, self.last_fn = layer_fn, last_fn
+        n = self.n
+        cnt = plan.count
+        self.buf_a = alloc(max(cnt[n - 1], 1))                       # layers n-1, n-3, ...
+        self.buf_b = alloc(max(cnt[n - 2], 1) if n >= 2 else 1)      # layers n-2, n-4, ...
+        b, e = plan.own[n][self.rank]
+        self.begin, self.end = b, e
+        self.probs = (alloc_real or (lambda k: torch.empty(k, dtype=torch.float64, device=self.buf_a.device)))(max(e - b, 1))[:e - b]
+        self.psum = torch.zeros(1, dtype=torch.float64, device=self.buf_a.device)
+        # static per-step schedule: for every exchange group the (peer, slice) lists of this rank
+        r = self.rank
+        self._xfer = {}
+        for k in range(plan.k0, n):
+            for g in range(plan.groups(k)):
+                sends = [(q, seg) for q in range(self.world) for seg in plan.transfers(k, g, r, q)]
+                recvs = [(q, seg) for q in range(self.world) for seg in plan.transfers(k, g, q, r)]
+                self._xfer[(k, g)] = (sends, recvs)
+        self.bytes_received = 16 * plan.recv_elems(r)
+        self.bytes_sent = 16 * plan.send_elems(r)
+
+    def _buf(self, k: int):
+        return self.buf_a if (self.n - 1 - k) % 2 == 0 else self.buf_b
+
+    def _exchange(self, k: int, g: int, buf):
+        sends, recvs = self._xfer[(k, g)]
+        if not sends and not recvs:
+            return None
+        flat = torch.view_as_real(buf)
+        ops = []
+        for q, (lo, hi) in recvs:
+            ops.append(dist.P2POp(dist.irecv, flat[lo:hi], q, self.group))
+        for q, (lo, hi) in sends:
+            ops.append(dist.P2POp(dist.isend, flat[lo:hi], q, self.group))
+        return [dist.batch_isend_irecv(ops), False]
+
+    @staticmethod
+    def _wait(group):
+        """wait once for an exchange group (a second wait() on a completed gloo send / recv never returns)"""
+        if group is None or group[1]:
+            return
+        for w in group[0]:
+            w.wait()
+        group[1] = True
+
+    def run(self, reduce_sum: bool = True, on_last_piece=None):
+        """one step: returns (probabilities of [begin, end), (begin, end), sum(p))"""
+        plan, n, r = self.plan, self.n, self.rank
+        cnt = plan.count
+        self.psum.zero_()
+        parent = None
+        for k in range(1, plan.k0):                                   # replicated layers
+            buf = self._buf(k)
+            self.layer_fn(k, self.order[k - 1], parent, buf[:cnt[k]], 0, cnt[k])
+            parent = buf
+        groups = []                                                   # exchange groups that followed layer k-1, in order
+        older = []                                                    # ... and layer k-2: its buffer is about to be rewritten
+        for k in range(plan.k0, n + 1):
+            buf = self._buf(k) if k < n else None
+            for w in older:                                           # (always complete by now; keeps the re-use explicit)
+                self._wait(w)
+            for j, (b, e) in enumerate(plan.piece[k][r]):
+                if j < len(groups):
+                    self._wait(groups[j])                             # the parents child piece j needs have arrived
+                if e <= b:
+                    continue
+                if k < n:
+                    self.layer_fn(k, self.order[k - 1], parent, buf[b:e], b, e)
+                else:
+                    if on_last_piece is not None:
+                        on_last_piece(j, "begin")
+                    self.last_fn(k, self.order[k - 1], parent, self.probs[b - self.begin:e - self.begin], self.psum, b, e)
+                    if on_last_piece is not None:
+                        on_last_piece(j, "end")
+            for w in groups[len(plan.piece[k][r]):]:
+                self._wait(w)
+            older = groups
+            groups = [self._exchange(k, g, buf) for g in range(plan.groups(k))] if k < n else []
+            parent = buf
+        for w in older:
+            self._wait(w)
+        if reduce_sum and self.world > 1:
+            dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
+        return self.probs, (self.begin, self.end), self.psum
+
+
+def engine_exchange_chain(engine, U_ref, in_state, group=None, pieces: int = 4, shard_min: int = 1 << 23, boundaries=None):
+    """Device instantiation of ExchangeChain: kernels from libfock_b200.so, NCCL send / recv over NVLink.  ``U_ref`` is a
+    one-element list holding the device unitary, so that a step can swap it without rebuilding plan and buffers."""
+    from .engine import prodnfact
+    occ = [int(x) for x in in_state]
+    m, n = len(occ), sum(occ)
+    _rank, world = _world(group)
+    order = engine.slos_order(occ)
+    inf = prodnfact(occ)
+    plan = ExchangePlan(m, n, world, pieces=pieces, shard_min=shard_min, boundaries=boundaries)
+    vac = torch.ones(1, dtype=torch.complex128, device=engine.device)
+
+    def alloc(k):
+        return torch.empty(k, dtype=torch.complex128, device=engine.device)
+
+    def layer_fn(k, mk, parent, out, b, e):
+        engine.slos_layer(m, k, U_ref[0], mk, vac if parent is None else parent[:plan.count[k - 1]], child=out, child_begin=b, child_end=e)
+
+    def last_fn(k, mk, parent, out, psum, b, e):
+        engine.slos_layer_probs(m, k, U_ref[0], mk, vac if parent is None else parent[:plan.count[k - 1]], inf, probs=out, psum=psum,
+                                child_begin=b, child_end=e)
+
+    return ExchangeChain(m, occ, order, plan, alloc, layer_fn, last_fn, group)
+
+
 def permanents_sharded(perm_fn, mats: torch.Tensor, group=None):
     """Batch of permanents over ranks.  perm_fn(mats, gray_begin, gray_end) -> (B,) complex tensor (partial sums for a
     Gray sub-range, already scaled).  B >= world: split by matrix + all-gather; else split the Gray range + all-reduce."""

@@ -64,6 +64,17 @@ class FockEngine:
     def launch_count(self) -> int:
         return int(self.lib.fock_launch_count(self.ctx))
 
+    def profile_events(self, begin: torch.cuda.Event | None, end: torch.cuda.Event | None):
+        """CUDA events recorded around every probability-layer launch of this engine (C ABI fock_profile_events) until
+        called again with (None, None).  The events must have been recorded once (torch creates the handle lazily)."""
+        if begin is None:
+            check(self.lib.fock_profile_events(self.ctx, None, None), "fock_profile_events")
+            return
+        for ev in (begin, end):
+            if not ev.cuda_event:
+                ev.record(torch.cuda.current_stream(self.device))
+        check(self.lib.fock_profile_events(self.ctx, C.c_void_p(begin.cuda_event), C.c_void_p(end.cuda_event)), "fock_profile_events")
+
     def check_status(self):
         check(self.lib.fock_check_status(self.ctx, self._stream()), "fock_check_status")
 

@@ -170,3 +170,66 @@ def test_world2_windowed_partition_agreement(tmp_path):
     port = _free_port()
     mp.spawn(_windowed_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"wok{r}")) for r in range(world))
+
+
+def _exchange_worker(rank, world, port, outdir, pieces, fractions):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from perceval_b200 import dist as pdist
+
+    m, in_state = 8, (1, 1, 0, 1, 1, 0, 1, 1)
+    n = sum(in_state)
+    u = oracle.random_unitary(m, seed=10)
+    ref = oracle.slos_probs(u, in_state)
+    order = oracle.slos_order(in_state)
+    lib = oracle.lib()
+    plan = pdist.ExchangePlan(m, n, world, pieces=pieces, shard_min=30, fractions=fractions)
+    assert 1 <= plan.k0 < n
+    # the own ranges tile every sharded layer, and what r receives from q is what q sends to r
+    for k in range(plan.k0, n + 1):
+        assert plan.own[k][0][0] == 0 and plan.own[k][-1][1] == plan.count[k]
+        assert all(a[1] == b[0] for a, b in zip(plan.own[k], plan.own[k][1:]))
+    assert sum(plan.recv_elems(r) for r in range(world)) == sum(plan.send_elems(r) for r in range(world))
+
+    def alloc(k):
+        return torch.full((k,), float("nan"), dtype=torch.complex128)     # a parent that was never written poisons its children
+
+    def layer_fn(k, mk, parent, out, b, e):
+        parent_np = np.ones(1, dtype=np.complex128) if parent is None else parent[:oracle.count(m, k - 1)].numpy()
+        child = np.empty(e - b, dtype=np.complex128)
+        lib.orc_slos_layer_gather(m, k, oracle._p(oracle._u(u)), mk, oracle._p(np.ascontiguousarray(parent_np)), oracle._p(child), b, e)
+        out.copy_(torch.from_numpy(child))
+
+    def last_fn(k, mk, parent, out, psum, b, e):
+        c = torch.empty(e - b, dtype=torch.complex128)
+        layer_fn(k, mk, parent, c, b, e)
+        states = oracle.unrank_batch(m, k, np.arange(b, e, dtype=np.uint64))
+        f = np.array([oracle.prodnfact(s) for s in states])
+        p = (np.abs(c.numpy()) ** 2) * f / oracle.prodnfact(in_state)
+        out.copy_(torch.from_numpy(p))
+        psum += float(p.sum())
+
+    chain = pdist.ExchangeChain(m, in_state, order, plan, alloc, layer_fn, last_fn)
+    for _ in range(2):                                                       # a second step re-uses buffers and plan
+        chain.buf_a.fill_(float("nan"))
+        chain.buf_b.fill_(float("nan"))
+        probs, (b, e), psum = chain.run()
+        assert not torch.isnan(probs).any()
+        assert np.abs(probs.numpy() - ref[b:e]).max() < 1e-14
+        assert abs(psum.item() - 1.0) < 1e-12
+    assert chain.bytes_received == 16 * plan.recv_elems(rank) and chain.bytes_received > 0
+    open(os.path.join(outdir, f"xok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,pieces,fractions", [(2, 1, None), (2, 3, None), (3, 4, None), (2, 2, [0.0, 0.3, 1.0])])
+def test_exchange_chain_gloo(tmp_path, world, pieces, fractions):
+    """Owner-computes + halo exchange at world size 2 / 3 on CPU: every rank computes only its own range of
+    every sharded layer, receives exactly the parent slices its children need (NaN-poisoned buffers: a parent that was
+    neither owned nor received would surface), and the slices reproduce the oracle's distribution."""
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path), pieces, fractions), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"xok{r}")) for r in range(world))
