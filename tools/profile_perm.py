@@ -1,7 +1,7 @@
 """Runs one Glynn batch and one Clifford&Clifford batch (for ncu capture) -- profiling helper, run under gpurun + ncu."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceval_b200.engine import FockEngine
 from perceval_b200.circuit import random_unitary
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30

@@ -1,7 +1,7 @@
 """Runs one SLOS chain (for ncu capture of the last-layer kernel) -- profiling helper, run under gpurun + ncu."""
 import os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceval_b200.engine import FockEngine
 from perceval_b200.circuit import random_unitary
 n, m = int(sys.argv[1]), int(sys.argv[2])

@@ -1,7 +1,7 @@
 """Times batched Glynn permanents (tuning helper, run under gpurun)."""
 import os, sys, json
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceval_b200.engine import FockEngine
 from perceval_b200.circuit import random_unitary
 eng = FockEngine.get(0)

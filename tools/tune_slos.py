@@ -1,7 +1,7 @@
 """Times the SLOS chain / last layer for one tail width (FOCK_SLOS_TAIL) -- tuning helper, run under gpurun."""
 import os, sys, json, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceval_b200.engine import FockEngine, prodnfact
 from perceval_b200.circuit import random_unitary
 n, m = int(sys.argv[1]), int(sys.argv[2])
