@@ -338,6 +338,30 @@ def spot_check(torch, eng, u_np, in_state, probs, begin, end, count, seed):
     return float(np.abs(got - ref).max() / max(ref.max(), 1e-300))
 
 
+def spot_check_slab(torch, chain, u_np, in_state, count, seed):
+    """the same check for the slab partition, whose output is stored compactly in slab-major order (chain.out_slices)"""
+    import oracle
+    from perceval_b200 import partition as P
+    if count <= 0 or chain.probs.numel() == 0:
+        return 0.0
+    L = chain.plan.layout
+    n = chain.n
+    rng = np.random.default_rng(seed)
+    pos = rng.integers(0, chain.probs.numel(), count)
+    got = chain.probs[torch.from_numpy(pos).to(chain.probs.device)].cpu().numpy()
+    ref = []
+    for x in pos:
+        for w, a, b, off, ln in chain.out_slices:
+            if off <= x < off + ln:
+                S = L.S[n][w]
+                rho, t = a + (x - off) // S, (x - off) % S
+                state = P.unrank(L.p, w, int(rho)) + P.unrank(L.D, n - w, int(t))
+                ref.append(abs(oracle.naive_amplitude(u_np, tuple(in_state), tuple(state))) ** 2)
+                break
+    ref = np.array(ref)
+    return float(np.abs(got - ref).max() / max(ref.max(), 1e-300))
+
+
 # ------------------------------------------------------------------------------------------------ SLOS, one GPU: through the backend
 def run_slos_single(args, torch, rank, local_rank, barrier, rmax):
     import perceval_b200 as pb
@@ -465,7 +489,7 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     if partition == "auto":
         free, _tot = torch.cuda.mem_get_info(dev)
         full_buffers = 16 * (eng.count(m, n - 1) + max(eng.count(m, n - 2), 1)) + 8 * (N // world + 1)
-        partition = ("exchange" if world <= args.exchange_max_world else "windowed") if full_buffers < 0.85 * free else "windowed"
+        partition = "slab" if full_buffers < 0.85 * free else "windowed"
     events = []          # (begin, end) CUDA events around every last-layer launch of a step
     alg_bytes = [0.0]
 
@@ -484,6 +508,34 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
         desc = (f"recompute-window: {world} ranks x {chain.sub} sub-shards, every rank recomputes the parents its output range needs, no "
                 f"exchange step; workspace {chain.bytes / 1e9:.1f} GB on rank 0")
         nvlink = {"bytes_received_per_step": 0, "bytes_sent_per_step": 0}
+    elif partition == "slab":
+        from perceval_b200 import slab as pslab
+        U_ref = [U]
+        chain = pslab.engine_slab_chain(eng, U_ref, in_state, shard_min=args.shard_min)
+        plan = chain.plan
+        b, e = 0, chain.probs.numel()          # compact slab-major storage of this rank's prefixes (chain.out_slices)
+        get_probs = lambda: chain.probs
+        get_sum = lambda: chain.psum
+
+        def on_last(what):
+            evt = torch.cuda.Event(enable_timing=True)
+            evt.record()
+            if what == "begin":
+                events.append([evt, None])
+            else:
+                events[-1][1] = evt
+
+        def step(Udev=U):
+            U_ref[0] = Udev
+            chain.run(reduce_sum=False, on_last=on_last)
+        Lh = plan.layout
+        rows_last = sum((hi - lo) * Lh.S[n - 1][w - 1] for w, segs in plan.rows[rank].items() for lo, hi in segs)
+        tails_last = sum((bb - aa) * Lh.S[n - 1][w] for w, aa, bb in plan.own[rank] if w <= n - 1)
+        alg_bytes[0] = 16.0 * (rows_last + tails_last) + 8.0 * (e - b)
+        desc = (f"slab partition: layers < {plan.k0} replicated; layers {plan.k0}..{n} stored slab-major (prefix weight over the first "
+                f"{Lh.p} modes, prefix rank, tail rank), every rank owns a fixed run of prefixes, tail parents local, prefix rows "
+                f"received over NVLink (NCCL send/recv of contiguous slab slices); output stays sharded in slab-major order")
+        nvlink = {"bytes_received_per_step": int(chain.bytes_received), "bytes_sent_per_step": int(chain.bytes_sent)}
     else:
         U_ref = [U]
         shard_min = (1 << 62) if partition == "replicate" else args.shard_min
@@ -521,7 +573,12 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     dist.all_reduce(psum)
     total_p = float(psum.item())
     assert abs(total_p - 1.0) < 1e-9, f"sum(p) = {total_p}"
-    worst = rmax(spot_check(torch, eng, u_np, in_state, get_probs(), b, e, args.spot, 1234 + rank)) if args.spot else None
+    if not args.spot:
+        worst = None
+    elif partition == "slab":
+        worst = rmax(spot_check_slab(torch, chain, u_np, in_state, args.spot, 1234 + rank))
+    else:
+        worst = rmax(spot_check(torch, eng, u_np, in_state, get_probs(), b, e, args.spot, 1234 + rank))
     if worst is not None:
         assert worst < 1e-9, worst
 
@@ -790,10 +847,10 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="permanents: matrices per step (whole job)")
     ap.add_argument("--samples", type=int, default=100000, help="cc2017: samples per step (whole job)")
     ap.add_argument("--e2e-pieces", type=int, default=8)
-    ap.add_argument("--partition", default="auto", choices=["auto", "replicate", "exchange", "windowed"],
-                    help="N > 1: replicate = lower layers on every rank, output layer sharded; exchange = owner-computes + NVLink halo "
-                         "exchange; windowed = recompute-window chain (no exchange, the only one that fits 14/28)")
-    ap.add_argument("--exchange-max-world", type=int, default=4, help="auto: largest world size that takes the exchange partition")
+    ap.add_argument("--partition", default="auto", choices=["auto", "replicate", "exchange", "slab", "windowed"],
+                    help="N > 1: slab = prefix slabs owned by rank, prefix rows over NVLink (default when two whole layers fit); "
+                         "replicate = lower layers on every rank, output layer sharded by rank range; exchange = rank ranges + NVLink "
+                         "halo exchange; windowed = recompute-window chain (no exchange, the only one that fits 14/28)")
     ap.add_argument("--pieces", type=int, default=4, help="exchange: child pieces / exchange groups per layer")
     ap.add_argument("--shard-min", type=int, default=1 << 23, help="exchange: layers with fewer states are replicated")
     ap.add_argument("--sub", type=int, default=0, help="windowed: sub-shards per rank (0 = from free memory)")

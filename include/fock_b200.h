@@ -91,6 +91,18 @@ int slos_layer_probs_seg(fock_ctx *ctx, int m, int k, const double *d_U, int mk,
                          const uint64_t *h_parent_seg, double *d_child, double *d_probs, double *d_sum, double in_prodnfact,
                          uint64_t child_begin, uint64_t child_end, void *stream);
 
+/* One layer in SLAB-MAJOR layout -- the layout of the multi-GPU slab partition (no reference counterpart: the reference keeps
+ * every layer whole in host memory, _slos.py:44).  The modes are split as in the tile kernels into a prefix of p modes and a
+ * tail of m - p; a layer is stored by prefix weight w ("slab"), then prefix rank rho in FSArray(p, w), then tail rank t in
+ * FSArray(m - p, photons - w):  index = slab_off[w] + rho * |FSArray(m - p, photons - w)| + t.  h_rho_ranges holds, per
+ * w = 0..k, the prefixes [lo, hi) of the child layer to compute (2 (k+1) entries); h_parent_slab_off the element offset of
+ * parent slab w' (k entries, relative to d_parent); h_child_slab_off that of child slab w (k+1 entries, relative to d_child /
+ * d_probs; offsets are taken modulo 2^64, so compact per-rank layouts work too).  Same gather as slos_layer; d_child and/or
+ * d_probs (+ d_sum) as in slos_layer_probs.  p must be the prefix width the library uses for m modes (m - 16 for m >= 20). */
+int slos_layer_slab(fock_ctx *ctx, int m, int k, int p, const double *d_U, int mk, const double *d_parent, double *d_child,
+                    double *d_probs, double *d_sum, double in_prodnfact, const uint64_t *h_rho_ranges,
+                    const uint64_t *h_parent_slab_off, const uint64_t *h_child_slab_off, void *stream);
+
 /* One layer over a PRUNED rank space (masks / heralds; replaces the layers the reference builds on xq.FSArray(m, k, mask),
  * perceval/backends/_slos.py:156-166): d_child_ranks / d_parent_ranks are the ascending kept ranks of FSArray(m, k) /
  * FSArray(m, k-1), d_parent the packed parent coefficients in that order.  Writes, per kept child, any of: the packed

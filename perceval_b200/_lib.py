@@ -33,6 +33,7 @@ SYMBOLS = [
     ("slos_layer_probs", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _u64, _u64, _vp, _vp, _vp, _dbl, _u64, _u64, _vp]),
     ("slos_layer_seg", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _u64, _u64, _vp]),
     ("slos_layer_probs_seg", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _dbl, _u64, _u64, _vp]),
+    ("slos_layer_slab", _i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     ("slos_layer_masked", _i32, [_vp, _i32, _i32, _vp, _i32, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _dbl, _vp]),
     ("slos_probs_epilogue", _i32, [_vp, _i32, _i32, _vp, _dbl, _vp, _vp, _u64, _u64, _vp]),
     ("slos_amplitudes_epilogue", _i32, [_vp, _i32, _i32, _vp, _dbl, _vp, _u64, _u64, _vp]),

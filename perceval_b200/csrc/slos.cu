@@ -348,14 +348,27 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
                     ++nz;
                     pf *= s_fact[si];
                 }
-                base += s_bt[(m - 1 - i) * FOCK_TMAX + Tfull];
-                if (Tfull > 0) E += s_dt[(m - 1 - i) * FOCK_TMAX + Tfull];
+                if (a.slab) {   // slab-major: E is the PREFIX-local rank difference (same identity on FS(p, w))
+                    if (T > 0) E += s_dt[(p - 1 - i) * FOCK_TMAX + T];
+                } else {
+                    base += s_bt[(m - 1 - i) * FOCK_TMAX + Tfull];
+                    if (Tfull > 0) E += s_dt[(m - 1 - i) * FOCK_TMAX + Tfull];
+                }
                 Tprev = T;
             }
-            for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
+            uint64_t tb;
+            if (a.slab) {
+                const uint64_t rho = rho0 + tid;
+                base = a.cls[ci].coff + rho * S;
+                for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = a.cls[ci].roff + (rho - e_pb[tid * maxnz + e]) * S;
+                tb = a.cls[ci].toff + rho * a.cls[ci].Sp;
+            } else {
+                for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
+                tb = base - E;   // only meaningful (and only used) when u >= 1
+            }
             TileDesc td;
             td.cbase = base;
-            td.tbase = base - E;   // only meaningful (and only used) when u >= 1
+            td.tbase = tb;
             td.pfact = pf;
             td.nz = nz;
             td.pad = 0;
@@ -518,10 +531,16 @@ static int launch_tile(fock_ctx *c, TileArgs &a, bool want_child, bool want_prob
     return fock_check_cuda(cudaGetLastError(), "slos_tile_kernel");
 }
 
+// slab-major layouts (slos_layer_slab): per prefix weight w the prefixes [rho[2w], rho[2w+1]) to compute, the element offset of
+// parent slab w' (w' = 0..k-1) and of child slab w (w = 0..k); index(w, rho, t) = off[w] + rho * |FS(D, photons - w)| + t
+struct SlabSpec {
+    const uint64_t *rho, *parent_off, *child_off;
+};
+
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
                             uint64_t ce, cudaStream_t st, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
-                            uint64_t gap_e = UINT64_MAX) {
+                            uint64_t gap_e = UINT64_MAX, const SlabSpec *slab = nullptr) {
     // gfilter: 0 = every class (tile kernel), 1 = only classes whose tail block fills a CTA (S >= 256) in the hybrid thin
     //          kernel (slos_thin.cu), 2 = only the small classes (S < 256) in the tile kernel
     const int p = m - D;
@@ -543,7 +562,8 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     a.inv_in_fact = 1.0 / in_prodnfact;
     a.cbegin = cb; a.cend = ce;
     a.status = c->d_status;
-    const bool full = (cb == 0 && ce == fock_count(m, k));
+    a.slab = slab ? 1 : 0;
+    const bool full = slab != nullptr || (cb == 0 && ce == fock_count(m, k));
     uint64_t items = 0;
     int ncls = 0;
     // classes with small tail blocks first: their CTAs walk many prefixes with little work each and would otherwise run
@@ -554,7 +574,11 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
         if ((gfilter == 1 && S64 < TILE_BLOCK) || (gfilter == 2 && S64 >= TILE_BLOCK)) continue;
         uint64_t lo = 0, hi = np_total;
-        if (!full) {
+        if (slab) {
+            lo = slab->rho[2 * w];
+            hi = slab->rho[2 * w + 1];
+            FOCK_REQUIRE(lo <= hi && hi <= np_total, FOCK_ERR_ARG, "slos_layer_slab: bad prefix range for weight %d", w);
+        } else if (!full) {
             // prefixes whose tile [base, base+S) intersects [cb, ce); base is increasing in rho
             uint64_t l = 0, h = np_total;
             while (l < h) { uint64_t mid = (l + h) / 2; if (host_prefix_base(m, p, w, u, mid) + S64 > cb) h = mid; else l = mid + 1; }
@@ -570,6 +594,12 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
         tc.G = S64 >= TILE_BLOCK ? 1u : (uint32_t)(TILE_BLOCK / S64);
         tc.nchunks = S64 >= TILE_BLOCK ? (uint32_t)((S64 + TILE_BLOCK - 1) / TILE_BLOCK) : 1u;
         tc.rho_lo = lo; tc.np = hi - lo;
+        if (slab) {
+            tc.coff = slab->child_off[w];
+            tc.roff = w >= 1 ? slab->parent_off[w - 1] : 0;
+            tc.toff = u >= 1 ? slab->parent_off[w] : 0;
+            tc.Sp = u >= 1 ? fock_count(D, u - 1) : 0;
+        }
         // prefixes per CTA: 128 sweep steps for full tiles (512: 21.0 ms, 128: 20.5 ms for the 12/24 chain -- mid-size layers need the CTAs); packed small tiles (G prefixes per step) get short items so that
         // they spread over many CTAs instead of one CTA walking tens of thousands of prefixes
         tc.per_item = (uint64_t)(tc.G > 1 ? 32 : 128) * tc.G;
@@ -710,6 +740,46 @@ extern "C" int slos_layer_probs_seg(fock_ctx *c, int m, int k, const double *d_U
     const bool two = seg[2] < seg[3];
     return slos_layer_impl(c, m, k, d_U, mk, d_parent, seg[0], two ? seg[3] : seg[1], d_child, d_probs, d_sum, in_prodnfact, cb, ce,
                            stream, "slos_layer_probs_seg", two ? seg[1] : UINT64_MAX, two ? seg[2] : UINT64_MAX);
+}
+
+// One layer in SLAB-MAJOR layout (multi-GPU slab partition, perceval_b200/slab.py): parent and child are stored by prefix
+// weight ("slab"), then prefix rank, then tail rank; only the prefixes [rho_lo, rho_hi) of every slab are computed.  The same
+// gather as slos_layer (reference _slos.py:91-97), with the addresses of the aligned prefix rows and of the tail-parent block
+// taken from the slab offsets instead of the FSArray rank.
+extern "C" int slos_layer_slab(fock_ctx *c, int m, int k, int p, const double *d_U, int mk, const double *d_parent, double *d_child,
+                               double *d_probs, double *d_sum, double in_prodnfact, const uint64_t *h_rho_ranges,
+                               const uint64_t *h_parent_slab_off, const uint64_t *h_child_slab_off, void *stream) {
+    if (int rc = slos_check("slos_layer_slab", c, m, k)) return rc;
+    FOCK_REQUIRE(k >= 1, FOCK_ERR_ARG, "slos_layer_slab: child layer must hold >= 1 photon");
+    FOCK_REQUIRE(mk >= 0 && mk < m, FOCK_ERR_ARG, "slos_layer_slab: input mode %d outside [0,%d)", mk, m);
+    FOCK_REQUIRE(d_U && d_parent && (d_child || d_probs), FOCK_ERR_ARG, "slos_layer_slab: NULL device pointer");
+    FOCK_REQUIRE(h_rho_ranges && h_parent_slab_off && h_child_slab_off, FOCK_ERR_ARG, "slos_layer_slab: NULL layout table");
+    FOCK_REQUIRE(d_probs == nullptr || in_prodnfact > 0, FOCK_ERR_ARG, "slos_layer_slab: in_prodnfact must be > 0");
+    const int D = slos_tail_modes(m);
+    FOCK_REQUIRE(D > 0 && p == m - D, FOCK_ERR_ARG, "slos_layer_slab: the prefix of m = %d modes holds %d modes (got %d)", m, m - D, p);
+    FOCK_REQUIRE(((uintptr_t)d_parent & 15) == 0, FOCK_ERR_ARG, "slos_layer_slab: parent buffer must be 16-byte aligned");
+    ScopedDevice sd(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    struct EventBracket {
+        cudaEvent_t e;
+        cudaStream_t s;
+        EventBracket(cudaEvent_t b, cudaEvent_t e_, cudaStream_t s_) : e(e_), s(s_) { if (b) cudaEventRecord(b, s_); }
+        ~EventBracket() { if (e) cudaEventRecord(e, s); }
+    } bracket(d_probs ? c->ev_begin : nullptr, d_probs ? c->ev_end : nullptr, st);
+    SlabSpec spec{h_rho_ranges, h_parent_slab_off, h_child_slab_off};
+    uint64_t children = 0;
+    for (int w = 0; w <= k; ++w) children += (h_rho_ranges[2 * w + 1] - h_rho_ranges[2 * w]) * fock_count(D, k - w);
+    if (children == 0) return FOCK_OK;
+    const uint64_t np = fock_count(m, k - 1), nc = fock_count(m, k);
+    const bool thin = d_probs != nullptr && D == 16 && m - D <= 8 && children >= (1ull << 24) && slos_thin_supports(D, k);
+    if (thin) {
+        if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 1,
+                                      UINT64_MAX, UINT64_MAX, &spec)) return rc;
+        return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 2, UINT64_MAX,
+                                UINT64_MAX, &spec);
+    }
+    return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 0, UINT64_MAX,
+                            UINT64_MAX, &spec);
 }
 
 extern "C" int slos_probs_epilogue(fock_ctx *c, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,

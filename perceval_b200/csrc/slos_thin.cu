@@ -67,7 +67,7 @@ struct ThShared {
 #define TH6_LEAD 8
 
 template <int D, int WL, int WT, int MODE, bool RANGECHK>
-__device__ __forceinline__ void th6_sweep(const TileArgs &a, const ThShared &sh, const uint32_t pm, const uint32_t wm_lo, const uint32_t t,
+__device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl, const ThShared &sh, const uint32_t pm, const uint32_t wm_lo, const uint32_t t,
                                           const int u, const int w, const uint64_t rho_a, const uint64_t rho_b, const bool active,
                                           double &local_sum) {
     const int m = a.m, p = a.p, maxnz = a.maxnz;
@@ -103,14 +103,28 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const ThShared &sh,
                     ++nz;
                     pf *= th_factorial(si);
                 }
-                base += __ldg(bt + (m - 1 - i) * FOCK_TMAX + Tfull);
-                if (Tfull > 0) E += __ldg(dt + (m - 1 - i) * FOCK_TMAX + Tfull);
+                if (a.slab) {   // slab-major: E is the PREFIX-local rank difference (same identity on FS(p, w))
+                    if (T > 0) E += __ldg(dt + (p - 1 - i) * FOCK_TMAX + T);
+                } else {
+                    base += __ldg(bt + (m - 1 - i) * FOCK_TMAX + Tfull);
+                    if (Tfull > 0) E += __ldg(dt + (m - 1 - i) * FOCK_TMAX + Tfull);
+                }
                 Tprev = T;
             }
-            for (int e = 0; e < nz; ++e) sh.e_ptr[tid * maxnz + e] = (uint64_t)(parent_b + ((base - sh.e_ptr[tid * maxnz + e]) << 4));
+            uint64_t tb;
+            if (a.slab) {
+                const uint64_t rho = rho0 + tid;
+                base = cl.coff + rho * cl.S;
+                for (int e = 0; e < nz; ++e)
+                    sh.e_ptr[tid * maxnz + e] = (uint64_t)(parent_b + ((cl.roff + (rho - sh.e_ptr[tid * maxnz + e]) * cl.S) << 4));
+                tb = cl.toff + rho * cl.Sp;
+            } else {
+                for (int e = 0; e < nz; ++e) sh.e_ptr[tid * maxnz + e] = (uint64_t)(parent_b + ((base - sh.e_ptr[tid * maxnz + e]) << 4));
+                tb = base - E;
+            }
             ThDesc td;
             td.cbase = base;
-            td.tptr = parent_b + ((base - E) << 4);
+            td.tptr = parent_b + (tb << 4);
             td.pfact = pf;
             td.nz = nz;
             td.pad = 0;
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin6_kernel(const _
     const int nlead = __popc(wbits);
     const int ntrail = __reduce_max_sync(0xffffffffu, cnt_t);
     double local_sum = 0.0;
-#define TH6_SWEEP(WL, WT) th6_sweep<D, WL, WT, MODE, RANGECHK>(a, sh, pm, wm_lo, t, u, w, rho_a, rho_b, active, local_sum)
+#define TH6_SWEEP(WL, WT) th6_sweep<D, WL, WT, MODE, RANGECHK>(a, a.cls[ci], sh, pm, wm_lo, t, u, w, rho_a, rho_b, active, local_sum)
     if (nlead <= 4) {
         if (ntrail <= 4) TH6_SWEEP(4, 4);
         else TH6_SWEEP(4, 8);

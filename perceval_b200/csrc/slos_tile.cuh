@@ -10,6 +10,11 @@ struct TileClass {
     uint64_t rho_lo, np;      // prefix ranks [rho_lo, rho_lo + np) of FS(p, w) intersect the child range
     uint64_t item_begin;      // first work item (CTA index) of this class
     uint64_t per_item;        // prefixes per work item
+    // slab-major layouts (TileArgs::slab != 0): element offsets with  index(w, rho, t) = off + rho * S + t
+    uint64_t coff;            // child slab w          (block size S)
+    uint64_t roff;            // parent slab w - 1     (block size S: the aligned rows of the prefix modes)
+    uint64_t toff;            // parent slab w         (block size Sp: the tail-parent block of the same prefix)
+    uint64_t Sp;              // |FS(D, u - 1)|
 };
 
 struct TileArgs {
@@ -25,6 +30,7 @@ struct TileArgs {
     double inv_in_fact;
     uint64_t cbegin, cend;
     int *status;
+    int slab;                  // 0: parent and child in FSArray rank order; 1: slab-major (offsets in TileClass), see slos_layer_slab
     int uslot;                 // thin kernel: which constant-bank copy of the unitary column this launch reads
     TileClass cls[FOCK_TMAX];
     const uint64_t *tup[FOCK_TMAX];   // per class, the occupation tuple (4 bits / tail mode) of every tail rank

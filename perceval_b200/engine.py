@@ -192,6 +192,22 @@ class FockEngine:
                                             child_begin, child_end, self._stream()), "slos_layer_probs_seg")
         return probs
 
+    def slos_layer_slab(self, m: int, k: int, p: int, U: torch.Tensor, mk: int, parent: torch.Tensor, rho_ranges, parent_off, child_off,
+                        child: torch.Tensor | None = None, probs: torch.Tensor | None = None, psum: torch.Tensor | None = None,
+                        in_prodnfact: float = 1.0):
+        """One layer in slab-major layout (C ABI slos_layer_slab; perceval_b200/slab.py): ``rho_ranges`` = [(lo, hi)] per prefix
+        weight 0..k, ``parent_off`` / ``child_off`` = element offsets of the parent / child slabs inside ``parent`` and
+        ``child`` / ``probs`` (Python ints, taken modulo 2^64)."""
+        assert len(rho_ranges) == k + 1 and len(parent_off) >= k and len(child_off) >= k + 1
+        mask = (1 << 64) - 1
+        rr = np.array([x & mask for ab in rho_ranges for x in ab], dtype=np.uint64)
+        po = np.array([x & mask for x in parent_off[:k]] or [0], dtype=np.uint64)
+        co = np.array([x & mask for x in child_off[:k + 1]], dtype=np.uint64)
+        check(self.lib.slos_layer_slab(self.ctx, m, k, p, U.data_ptr(), mk, parent.data_ptr(), child.data_ptr() if child is not None else None,
+                                       probs.data_ptr() if probs is not None else None, psum.data_ptr() if psum is not None else None,
+                                       float(in_prodnfact), rr.ctypes.data_as(C.c_void_p), po.ctypes.data_as(C.c_void_p),
+                                       co.ctypes.data_as(C.c_void_p), self._stream()), "slos_layer_slab")
+
     def slos_layer_masked(self, m: int, k: int, U: torch.Tensor, mk: int, parent_ranks: torch.Tensor, parent: torch.Tensor,
                           child_ranks: torch.Tensor, in_prodnfact: float = 1.0, want_coefs: bool = True, want_probs: bool = False,
                           want_amps: bool = False, psum: torch.Tensor | None = None):

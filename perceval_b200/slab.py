@@ -1,0 +1,343 @@
+"""Slab partition of the SLOS chain for several GPUs: owner-computes on prefix slabs, halo = parent rows only.
+
+Layout.  The m modes are split, exactly as in the tile kernels, into a PREFIX (first p = m - D modes) and a TAIL (last D).
+A layer k is stored SLAB-MAJOR: slab w (= photons in the prefix, 0..k) holds, for every prefix rho of FS(p, w) in FSArray
+order, the block of the S(k, w) = |FS(D, k - w)| tails in FSArray order:
+
+    index(k; w, rho, t) = slab_off[k][w] + rho * S(k, w) + t
+
+(a permutation of the FSArray rank order by whole prefix blocks; `rank_to_slab` / `slab_to_rank` convert).  One SLOS step
+then reads, for child (w, rho, t):  tail-mode parents from block (w, rho) of layer k-1 -- the SAME prefix -- and
+prefix-mode parents from the aligned rows (w-1, rho', t), rho' = rank of (prefix - e_j) in FS(p, w-1)
+(reference perceval/backends/_slos.py:91-97 read as a gather; kernels: slos_layer_slab in csrc/slos.cu).
+
+Ownership.  Rank q owns a contiguous run of prefixes in slab-major order (w ascending, rho ascending), THE SAME for every
+layer, cut so that the output layer is balanced.  Tail-mode parents are therefore always local; what crosses NVLink are
+prefix-mode rows only: for every owned (w, [a, b)) the rho' window of slab w-1 (partition.parent_segments on the prefix
+space FS(p, w), exact) minus what the rank owns itself -- contiguous slices of the neighbours' slabs.  At 12 photons /
+24 modes on 8 GPUs a rank receives 1.0 GB for the output layer instead of the 1.6 - 3.0 GB of rank-contiguous ranges, every
+rank sends about what it receives (no hot sender), and nothing is recomputed.
+"""
+from __future__ import annotations
+
+from . import partition as P
+
+
+def tail_modes(m: int) -> int:
+    """tail width of the tile kernels (slos_tail_modes in csrc/slos.cu); 0: no tile kernel for this m"""
+    D = 16 if m >= 20 else (12 if m >= 16 else (8 if m >= 12 else (6 if m >= 8 else (4 if m >= 6 else 0))))
+    return D if D <= m - 1 else 0
+
+
+class SlabLayout:
+    def __init__(self, m: int, n: int):
+        self.m, self.n = m, n
+        self.D = tail_modes(m)
+        assert self.D > 0, f"slab layout needs m >= 6 (m = {m})"
+        self.p = m - self.D
+        self.nprefix = [P.count(self.p, w) for w in range(n + 1)]
+        # S[k][w], slab_off[k][w] for k = 0..n
+        self.S = [[P.count(self.D, k - w) for w in range(k + 1)] for k in range(n + 1)]
+        self.off = []
+        for k in range(n + 1):
+            o, acc = [], 0
+            for w in range(k + 1):
+                o.append(acc)
+                acc += self.nprefix[w] * self.S[k][w]
+            assert acc == P.count(m, k)
+            self.off.append(o)
+
+    def index(self, k: int, state) -> int:
+        """slab-major index of an occupation tuple of layer k"""
+        pre, tail = list(state[:self.p]), list(state[self.p:])
+        w = sum(pre)
+        return self.off[k][w] + P.rank(self.p, pre) * self.S[k][w] + P.rank(self.D, tail)
+
+    def rank_to_slab(self, k: int, ranks):
+        """numpy int64 slab-major indices of FSArray ranks of layer k (vectorised over whole prefix blocks)"""
+        import numpy as np
+        ranks = np.asarray(ranks, dtype=np.int64)
+        perm = self.permutation(k)
+        return perm[ranks]
+
+    def permutation(self, k: int):
+        """perm[rank] = slab-major index, for the whole layer k (host memory: 8 B per state -- tests and spot checks only)"""
+        import numpy as np
+        key = ("perm", k)
+        if not hasattr(self, "_cache"):
+            self._cache = {}
+        if key not in self._cache:
+            N = P.count(self.m, k)
+            perm = np.empty(N, dtype=np.int64)
+            r = 0
+            # FSArray order = prefixes in descending lexicographic order over ALL weights, each followed by its tail block
+            for pre in _prefixes_desc(self.p, k):
+                w = sum(pre)
+                S = self.S[k][w]
+                base = self.off[k][w] + P.rank(self.p, pre) * S
+                perm[r:r + S] = np.arange(base, base + S, dtype=np.int64)
+                r += S
+            assert r == N
+            self._cache[key] = perm
+        return self._cache[key]
+
+
+def _prefixes_desc(p: int, kmax: int):
+    """all prefixes of p modes with at most kmax photons, in the order they appear in FSArray(m, k) (descending lex)"""
+    def rec(i, left):
+        if i == p:
+            yield []
+            return
+        for a in range(left, -1, -1):
+            for rest in rec(i + 1, left - a):
+                yield [a] + rest
+    yield from rec(0, kmax)
+
+
+class SlabPlan:
+    """Ownership + halo lists, identical on every rank (pure integer arithmetic)."""
+
+    def __init__(self, m: int, n: int, world: int, shard_min: int = 1 << 23):
+        self.layout = L = SlabLayout(m, n)
+        self.m, self.n, self.world = m, n, world
+        cnt = [P.count(m, k) for k in range(n + 1)]
+        self.count = cnt
+        k0 = n
+        for k in range(1, n + 1):
+            if cnt[k] >= shard_min:
+                k0 = k
+                break
+        self.k0 = max(1, min(k0, n))
+        # contiguous runs of prefixes balanced on the output layer; own[q] = [(w, a, b)] with whole prefixes
+        total = cnt[n]
+        self.own = [[] for _ in range(world)]
+        cum, q = 0, 0
+        for w in range(n + 1):
+            sw, a = L.S[n][w], 0
+            while a < L.nprefix[w]:
+                room = total * (q + 1) // world - cum
+                take = min(L.nprefix[w] - a, max(1, -(-room // sw))) if (room > 0 or q == world - 1) else 0
+                if take == 0:
+                    q += 1
+                    continue
+                self.own[q].append((w, a, a + take))
+                cum += take * sw
+                a += take
+                if cum >= total * (q + 1) // world and q < world - 1:
+                    q += 1
+        # merge adjacent runs of the same slab
+        for q in range(world):
+            merged = []
+            for w, a, b in self.own[q]:
+                if merged and merged[-1][0] == w and merged[-1][2] == a:
+                    merged[-1] = (w, merged[-1][1], b)
+                else:
+                    merged.append((w, a, b))
+            self.own[q] = merged
+        self._owners = {}
+        for q in range(world):
+            for w, a, b in self.own[q]:
+                self._owners.setdefault(w, []).append((q, a, b))
+        # halo[q][w] = [(src, lo, hi)]: rho' ranges of slab w-1 that rank q reads through prefix modes but does not own
+        self.rows = [{} for _ in range(world)]      # rows[q][w] = merged rho' segments of slab w-1 needed by q's part of slab w
+        self.halo = [{} for _ in range(world)]
+        for q in range(world):
+            for w, a, b in self.own[q]:
+                if w == 0:
+                    continue
+                segs = P.parent_segments(L.p, w, [(a, b)], max_segments=4)
+                self.rows[q][w] = segs
+                need = []
+                for lo, hi in segs:
+                    for src, sa, sb in self._owners.get(w - 1, []):
+                        if src == q:
+                            continue
+                        x, y = max(lo, sa), min(hi, sb)
+                        if y > x:
+                            need.append((src, x, y))
+                self.halo[q][w] = need
+
+    def owner_ranges(self, w: int):
+        return self._owners.get(w, [])
+
+    def own_elems(self, k: int, q: int) -> int:
+        return sum((b - a) * self.layout.S[k][w] for w, a, b in self.own[q] if w <= k)
+
+    def transfers(self, k: int, src: int, dst: int):
+        """element slices [lo, hi) of layer k (slab-major) that ``src`` sends to ``dst`` after layer k (k0 <= k < n): the rows
+        dst's children of layer k+1 read through prefix modes; merged per slab"""
+        L = self.layout
+        out = []
+        for w in sorted(self.halo[dst].keys()):
+            if w - 1 > k or w > k + 1:
+                continue
+            S = L.S[k][w - 1]
+            for s_, lo, hi in self.halo[dst][w]:
+                if s_ == src:
+                    out.append((L.off[k][w - 1] + lo * S, L.off[k][w - 1] + hi * S))
+        return out
+
+    def recv_elems(self, q: int, k: int | None = None) -> int:
+        ks = [k] if k is not None else range(self.k0, self.n)
+        return sum(hi - lo for kk in ks for s_ in range(self.world) for lo, hi in self.transfers(kk, s_, q))
+
+    def send_elems(self, q: int, k: int | None = None) -> int:
+        ks = [k] if k is not None else range(self.k0, self.n)
+        return sum(hi - lo for kk in ks for d in range(self.world) for lo, hi in self.transfers(kk, q, d))
+
+    def rho_ranges(self, k: int, q: int):
+        """[(lo, hi)] per prefix weight w = 0..k: the prefixes of slab w that rank q computes at layer k ((0, 0): none)"""
+        rr = [(0, 0)] * (k + 1)
+        for w, a, b in self.own[q]:
+            if w <= k:
+                assert rr[w] == (0, 0)
+                rr[w] = (a, b)
+        return rr
+
+
+class SlabChain:
+    """One SLOS chain under SlabPlan on this rank (one process per GPU, torch.distributed).  The compute step is injected so
+    that the ownership / exchange logic runs on CPU with gloo in the tests:
+
+      full_fn(k, mk, parent_rank_order, out)                       replicated layer k < k0 in FSArray rank order
+      to_slab_fn(k, rank_order, out_slab)                          layer k0-1: rank order -> slab-major (whole layer)
+      slab_fn(k, mk, parent_slab, rho_ranges, parent_off, child_off, child, probs, psum)
+                                                                   this rank's prefixes of layer k, slab-major in and out
+
+    Layers k0-1 .. n-1 live in two full-size slab-major ping-pong buffers (global indexing: own parts are computed in place,
+    halos are received in place); the output probabilities are stored compactly, own slabs back to back (`out_slices`).
+    After layer k every rank sends, per consumer, the rows of its slabs that the consumer's children of layer k+1 read
+    through prefix modes: one NCCL send / recv group per layer, contiguous slices only.
+    """
+
+    def __init__(self, plan: SlabPlan, order, alloc, alloc_real, full_fn, to_slab_fn, slab_fn, rank: int, group=None):
+        import torch
+        self.plan, self.order, self.rank, self.group = plan, order, rank, group
+        L = plan.layout
+        n = plan.n
+        self.n = n
+        self.full_fn, self.to_slab_fn, self.slab_fn = full_fn, to_slab_fn, slab_fn
+        cnt = plan.count
+        self.buf_a = alloc(max(cnt[n - 1], 1))
+        self.buf_b = alloc(max(cnt[n - 2], 1) if n >= 2 else 1)
+        # compact output: own slabs of layer n back to back; child_off[w] such that index = off + rho * S + t
+        self.out_slices = []           # (w, rho_lo, rho_hi, offset, length)
+        self.out_off = [0] * (n + 1)
+        acc = 0
+        for w, a, b in plan.own[rank]:
+            ln = (b - a) * L.S[n][w]
+            self.out_slices.append((w, a, b, acc, ln))
+            self.out_off[w] = acc - a * L.S[n][w]
+            acc += ln
+        self.probs = alloc_real(max(acc, 1))[:acc]
+        self.psum = torch.zeros(1, dtype=torch.float64, device=self.probs.device)
+        self._xfer = {}
+        for k in range(plan.k0, n):
+            sends = [(q, seg) for q in range(plan.world) for seg in plan.transfers(k, rank, q)]
+            recvs = [(q, seg) for q in range(plan.world) for seg in plan.transfers(k, q, rank)]
+            self._xfer[k] = (sends, recvs)
+        self.bytes_received = 16 * plan.recv_elems(rank)
+        self.bytes_sent = 16 * plan.send_elems(rank)
+
+    def _buf(self, k: int):
+        return self.buf_a if (self.n - 1 - k) % 2 == 0 else self.buf_b
+
+    def _scratch(self, elems: int):
+        if getattr(self, "_scratch_buf", None) is None or self._scratch_buf.numel() < elems:
+            self._scratch_buf = self.buf_a.new_empty(elems)
+        return self._scratch_buf[:elems]
+
+    def _exchange(self, k: int, buf):
+        import torch
+        import torch.distributed as dist
+        sends, recvs = self._xfer[k]
+        if not sends and not recvs:
+            return []
+        flat = torch.view_as_real(buf)
+        ops = [dist.P2POp(dist.irecv, flat[lo:hi], q, self.group) for q, (lo, hi) in recvs]
+        ops += [dist.P2POp(dist.isend, flat[lo:hi], q, self.group) for q, (lo, hi) in sends]
+        return dist.batch_isend_irecv(ops)
+
+    def run(self, reduce_sum: bool = True, on_last=None):
+        """one step: returns (compact probabilities of this rank's slabs, sum(p))"""
+        import torch.distributed as dist
+        plan, n, r = self.plan, self.n, self.rank
+        L = plan.layout
+        cnt = plan.count
+        self.psum.zero_()
+        k0 = plan.k0
+        # replicated layers 1 .. k0-1 in rank order, ping-pong in the same two buffers
+        parent = None
+        for k in range(1, k0):
+            buf = self._buf(k)
+            self.full_fn(k, self.order[k - 1], parent, buf[:cnt[k]])
+            parent = buf[:cnt[k]]
+        # layer k0-1 to slab-major (in the other buffer), then the sharded layers
+        if k0 - 1 >= 1:
+            # permute through the other ping-pong buffer (free until layer k0 is written) and copy back in place
+            other = self._buf(k0)
+            scratch = other[:cnt[k0 - 1]] if other.numel() >= cnt[k0 - 1] else self._scratch(cnt[k0 - 1])
+            self.to_slab_fn(k0 - 1, parent, scratch)
+            self._buf(k0 - 1)[:cnt[k0 - 1]].copy_(scratch)
+            parent = self._buf(k0 - 1)
+        else:
+            parent = self._buf(0)
+            parent[:1] = 1.0               # the vacuum: one prefix of weight 0, one tail
+        works = []
+        for k in range(k0, n + 1):
+            for w_ in works:
+                w_.wait()
+            rr = plan.rho_ranges(k, r)
+            if k < n:
+                buf = self._buf(k)
+                self.slab_fn(k, self.order[k - 1], parent, rr, L.off[k - 1], L.off[k], buf, None, None)
+                works = self._exchange(k, buf)
+                parent = buf
+            else:
+                if on_last is not None:
+                    on_last("begin")
+                self.slab_fn(k, self.order[k - 1], parent, rr, L.off[k - 1], self.out_off, None, self.probs, self.psum)
+                if on_last is not None:
+                    on_last("end")
+                works = []
+        if reduce_sum and plan.world > 1:
+            dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
+        return self.probs, self.psum
+
+
+def engine_slab_chain(engine, U_ref, in_state, group=None, shard_min: int = 1 << 23):
+    """Device instantiation of SlabChain: kernels from libfock_b200.so (slos_layer, slos_layer_slab), NCCL send / recv."""
+    import torch
+    import torch.distributed as dist
+    from .engine import prodnfact
+    occ = [int(x) for x in in_state]
+    m, n = len(occ), sum(occ)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    plan = SlabPlan(m, n, world, shard_min=shard_min)
+    L = plan.layout
+    order = engine.slos_order(occ)
+    inf = prodnfact(occ)
+    vac = torch.ones(1, dtype=torch.complex128, device=engine.device)
+    perm_cache = {}
+
+    def alloc(k):
+        return torch.empty(k, dtype=torch.complex128, device=engine.device)
+
+    def alloc_real(k):
+        return torch.empty(k, dtype=torch.float64, device=engine.device)
+
+    def full_fn(k, mk, parent, out):
+        engine.slos_layer(m, k, U_ref[0], mk, vac if parent is None else parent, child=out)
+
+    def to_slab_fn(k, src, dst):
+        if k not in perm_cache:
+            perm_cache[k] = torch.from_numpy(L.permutation(k)).to(engine.device)
+        dst.index_copy_(0, perm_cache[k], src)
+
+    def slab_fn(k, mk, parent, rr, poff, coff, child, probs, psum):
+        engine.slos_layer_slab(m, k, L.p, U_ref[0], mk, parent, rr, poff, coff, child=child, probs=probs, psum=psum, in_prodnfact=inf)
+
+    return SlabChain(plan, order, alloc, alloc_real, full_fn, to_slab_fn, slab_fn, rank, group)

@@ -233,3 +233,95 @@ def test_exchange_chain_gloo(tmp_path, world, pieces, fractions):
     neither owned nor received would surface), and the slices reproduce the oracle's distribution."""
     mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path), pieces, fractions), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"xok{r}")) for r in range(world))
+
+
+def _slab_worker(rank, world, port, outdir, m, in_state, shard_min):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from perceval_b200 import slab
+
+    n = sum(in_state)
+    u = oracle.random_unitary(m, seed=12)
+    ref = oracle.slos_probs(u, in_state)
+    order = oracle.slos_order(in_state)
+    lib = oracle.lib()
+    plan = slab.SlabPlan(m, n, world, shard_min=shard_min)
+    L = plan.layout
+    assert 1 <= plan.k0 <= n
+    # ownership tiles the prefix space of every slab exactly once
+    for w in range(n + 1):
+        spans = sorted((a, b) for q in range(world) for ww, a, b in plan.own[q] if ww == w)
+        assert spans[0][0] == 0 and spans[-1][1] == L.nprefix[w] and all(x[1] == y[0] for x, y in zip(spans, spans[1:]))
+    assert sum(plan.recv_elems(q) for q in range(world)) == sum(plan.send_elems(q) for q in range(world))
+
+    def gather_layer(k, mk, parent_rank_order):
+        child = np.empty(oracle.count(m, k), dtype=np.complex128)
+        lib.orc_slos_layer_gather(m, k, oracle._p(oracle._u(u)), mk, oracle._p(np.ascontiguousarray(parent_rank_order)), oracle._p(child), 0, child.shape[0])
+        return child
+
+    def full_fn(k, mk, parent, out):
+        out.copy_(torch.from_numpy(gather_layer(k, mk, np.ones(1, dtype=np.complex128) if parent is None else parent.numpy())))
+
+    def to_slab_fn(k, src, dst):
+        dst.index_copy_(0, torch.from_numpy(L.permutation(k)), src)
+
+    def slab_fn(k, mk, parent, rr, poff, coff, child, probs, psum):
+        # emulate the slab kernel with the oracle: slab-major parent -> rank order (missing parents are NaN and poison exactly
+        # the children that read them), whole layer in rank order, then only this rank's prefixes are written
+        perm_p, perm_c = L.permutation(k - 1), L.permutation(k)
+        parent_ro = parent.numpy()[:oracle.count(m, k - 1)][perm_p]
+        child_ro = gather_layer(k, mk, parent_ro)
+        child_slab = np.empty_like(child_ro)
+        child_slab[perm_c] = child_ro
+        states_slab = None
+        for w, (lo, hi) in enumerate(rr):
+            if hi <= lo:
+                continue
+            S = L.S[k][w]
+            src = child_slab[L.off[k][w] + lo * S: L.off[k][w] + hi * S]
+            dst0 = coff[w] + lo * S
+            if child is not None:
+                child[dst0:dst0 + (hi - lo) * S] = torch.from_numpy(src)
+            if probs is not None:
+                if states_slab is None:
+                    st = oracle.enumerate_states(m, k)
+                    states_slab = np.empty_like(st)
+                    states_slab[perm_c] = st
+                ss = states_slab[L.off[k][w] + lo * S: L.off[k][w] + hi * S]
+                f = np.array([oracle.prodnfact(x) for x in ss])
+                p = (np.abs(src) ** 2) * f / oracle.prodnfact(in_state)
+                probs[dst0:dst0 + (hi - lo) * S] = torch.from_numpy(p)
+                psum += float(p.sum())
+
+    chain = slab.SlabChain(plan, order, lambda k: torch.full((k,), float("nan"), dtype=torch.complex128),
+                           lambda k: torch.full((k,), float("nan"), dtype=torch.float64), full_fn, to_slab_fn, slab_fn, rank)
+    ref_slab = np.empty_like(ref)
+    ref_slab[L.permutation(n)] = ref
+    for _ in range(2):
+        chain.buf_a.fill_(float("nan"))
+        chain.buf_b.fill_(float("nan"))
+        probs, psum = chain.run()
+        assert not torch.isnan(probs).any()
+        for w, a, b, off, ln in chain.out_slices:
+            S = L.S[n][w]
+            want = ref_slab[L.off[n][w] + a * S: L.off[n][w] + b * S]
+            assert np.abs(probs.numpy()[off:off + ln] - want).max() < 1e-14
+        assert abs(psum.item() - 1.0) < 1e-12
+    got = torch.tensor([float(probs.numel())])
+    dist.all_reduce(got)
+    assert int(got.item()) == ref.shape[0]
+    open(os.path.join(outdir, f"sok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,in_state,shard_min", [(2, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30), (3, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30),
+                                                        (2, 6, (2, 0, 1, 1, 0, 1), 5), (2, 8, (1, 1, 1, 1, 0, 0, 0, 0), 1 << 40)])
+def test_slab_chain_gloo(tmp_path, world, m, in_state, shard_min):
+    """Slab partition at world size 2 / 3 on CPU: fixed prefix ownership, tail parents local, prefix rows
+    exchanged as contiguous slab slices; NaN-poisoned buffers prove that every parent a rank reads was owned or received."""
+    mp.spawn(_slab_worker, args=(world, _free_port(), str(tmp_path), m, in_state, shard_min), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"sok{r}")) for r in range(world))

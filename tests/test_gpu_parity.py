@@ -504,3 +504,75 @@ def test_two_streams_thin_kernel(eng, oracle):
     for o, r in zip(outs, refs):
         assert torch.equal(o, r)
     eng.check_status()
+
+
+# ---------------------------------------------------------------- slab-major layout (multi-GPU slab partition)
+
+@pytest.mark.parametrize("m,k", [(8, 4), (12, 6), (16, 8), (20, 7), (24, 6)])
+def test_slos_layer_slab_equals_rank_order_layer(eng, oracle, m, k):
+    """slos_layer_slab (slab-major parent and child) == slos_layer (FSArray rank order) under the block permutation, bit for
+    bit (same kernels, same accumulation order), for whole layers, for partial prefix ranges with compact child offsets, and
+    for the fused probability epilogue; the rank-order layer itself is checked against the oracle."""
+    from perceval_b200 import slab
+    L = slab.SlabLayout(m, k)
+    u = oracle.random_unitary(m, seed=14)
+    U = eng.unitary(u)
+    Np, Nc = oracle.count(m, k - 1), oracle.count(m, k)
+    rng = np.random.default_rng(4)
+    parent = rng.standard_normal(Np) + 1j * rng.standard_normal(Np)
+    ref = eng.slos_layer(m, k, U, 2, torch.from_numpy(parent).cuda())
+    assert rel_err(ref.cpu().numpy(), oracle.slos_layer(m, k, u, 2, parent, scatter=False)) < 1e-13
+    perm_p = torch.from_numpy(L.permutation(k - 1)).cuda()
+    perm_c = torch.from_numpy(L.permutation(k)).cuda()
+    parent_slab = torch.empty(Np, dtype=torch.complex128, device="cuda")
+    parent_slab[perm_p] = torch.from_numpy(parent).cuda()
+    full = [(0, L.nprefix[w]) for w in range(k + 1)]
+    child_slab = torch.full((Nc,), float("nan"), dtype=torch.complex128, device="cuda")
+    eng.slos_layer_slab(m, k, L.p, U, 2, parent_slab, full, L.off[k - 1], L.off[k], child=child_slab)
+    assert torch.equal(child_slab[perm_c], ref)
+    # probabilities + sum
+    probs_ref = eng.slos_layer_probs(m, k, U, 2, torch.from_numpy(parent).cuda(), 2.0)
+    probs_slab = torch.empty(Nc, dtype=torch.float64, device="cuda")
+    psum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    eng.slos_layer_slab(m, k, L.p, U, 2, parent_slab, full, L.off[k - 1], L.off[k], probs=probs_slab, psum=psum, in_prodnfact=2.0)
+    assert torch.equal(probs_slab[perm_c], probs_ref)
+    assert abs(psum.item() - probs_ref.sum().item()) <= 1e-12 * probs_ref.sum().item()
+    # partial prefix ranges, compact output: slab w keeps prefixes [lo, hi), stored back to back
+    rr, coff, acc = [], [], 0
+    for w in range(k + 1):
+        lo, hi = L.nprefix[w] // 3, max(L.nprefix[w] // 3, (2 * L.nprefix[w] + 2) // 3)
+        rr.append((lo, hi))
+        coff.append(acc - lo * L.S[k][w])
+        acc += (hi - lo) * L.S[k][w]
+    compact = torch.full((max(acc, 1),), float("nan"), dtype=torch.complex128, device="cuda")
+    eng.slos_layer_slab(m, k, L.p, U, 2, parent_slab, rr, L.off[k - 1], coff, child=compact)
+    off = 0
+    for w, (lo, hi) in enumerate(rr):
+        S = L.S[k][w]
+        assert torch.equal(compact[off:off + (hi - lo) * S], child_slab[L.off[k][w] + lo * S:L.off[k][w] + hi * S])
+        off += (hi - lo) * S
+    eng.check_status()
+
+
+@pytest.mark.parametrize("m,st,shard_min", [(12, (1,) * 6 + (0,) * 6, 200), (16, (2, 1, 1, 1, 1) + (0,) * 11, 1000),
+                                            (22, (1,) * 11 + (0,) * 11, 1 << 20)])
+def test_slab_chain_single_rank_matches_distribution(eng, oracle, m, st, shard_min):
+    """engine_slab_chain with one rank (no exchange): the slab-major chain reproduces the rank-order distribution bit for
+    bit; at 11 photons / 22 modes its output layer runs the hybrid thin kernel in slab mode."""
+    from perceval_b200 import slab
+    n = sum(st)
+    U = eng.unitary(oracle.random_unitary(m, seed=15))
+    ref, s_ref, _ = eng.slos_probs(U, st)
+    chain = slab.engine_slab_chain(eng, [U], st, shard_min=shard_min)
+    assert chain.plan.k0 < n
+    probs, psum = chain.run()
+    L = chain.plan.layout
+    perm = torch.from_numpy(L.permutation(n)).cuda()
+    for w, a, b, off, ln in chain.out_slices:
+        S = L.S[n][w]
+        base = L.off[n][w] + a * S
+        want = torch.empty(ref.numel(), dtype=torch.float64, device="cuda")
+        want[perm] = ref
+        assert torch.equal(probs[off:off + ln], want[base:base + ln])
+    assert abs(psum.item() - 1.0) < 1e-12
+    eng.check_status()
