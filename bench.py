@@ -487,9 +487,11 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     N = eng.count(m, n)
     partition = args.partition
     if partition == "auto":
+        from perceval_b200 import slab as pslab
         free, _tot = torch.cuda.mem_get_info(dev)
-        full_buffers = 16 * (eng.count(m, n - 1) + max(eng.count(m, n - 2), 1)) + 8 * (N // world + 1)
-        partition = "slab" if full_buffers < 0.85 * free else "windowed"
+        sp = pslab.SlabPlan(m, n, world, shard_min=args.shard_min)
+        need = max(16 * sum(sp.buffer_elems(q)) + 8 * sp.own_elems(n, q) for q in range(world))
+        partition = "slab" if need < 0.85 * free else "windowed"
     events = []          # (begin, end) CUDA events around every last-layer launch of a step
     alg_bytes = [0.0]
 

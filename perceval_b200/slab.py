@@ -134,6 +134,7 @@ class SlabPlan:
                 else:
                     merged.append((w, a, b))
             self.own[q] = merged
+        self._storage = {}
         self._owners = {}
         for q in range(world):
             for w, a, b in self.own[q]:
@@ -163,27 +164,66 @@ class SlabPlan:
     def own_elems(self, k: int, q: int) -> int:
         return sum((b - a) * self.layout.S[k][w] for w, a, b in self.own[q] if w <= k)
 
+    def storage(self, k: int, q: int):
+        """Compact per-rank layout of layer k (k0-1 <= k <= n-1) on rank q: per prefix weight w the contiguous prefix range
+        [lo, hi) the rank holds -- its own prefixes (tail parents of its children of layer k+1, and what it computes itself)
+        together with the rows of slab w its children of slab w+1 read -- and the element offset ``base`` of (w, lo).
+        Layer k0-1 (replicated, then permuted to slab-major) is held whole.  Returns ([(lo, hi, base)] for w = 0..k, size)."""
+        key = (k, q)
+        if key not in self._storage:
+            L = self.layout
+            out, acc = [], 0
+            for w in range(k + 1):
+                if k < self.k0:
+                    lo, hi = 0, L.nprefix[w]
+                else:
+                    spans = [(a, b) for ww, a, b in self.own[q] if ww == w]
+                    if k < self.n:
+                        spans += self.rows[q].get(w + 1, [])
+                    lo = min((x for x, _ in spans), default=0)
+                    hi = max((y for _, y in spans), default=0)
+                out.append((lo, hi, acc))
+                acc += (hi - lo) * L.S[k][w]
+            self._storage[key] = (out, acc)
+        return self._storage[key]
+
+    def offsets(self, k: int, q: int):
+        """element offsets off[w] of rank q's compact layer k with index(w, rho, t) = off[w] + rho * S + t (may be negative)"""
+        L = self.layout
+        return [base - lo * L.S[k][w] for w, (lo, hi, base) in enumerate(self.storage(k, q)[0])]
+
     def transfers(self, k: int, src: int, dst: int):
-        """element slices [lo, hi) of layer k (slab-major) that ``src`` sends to ``dst`` after layer k (k0 <= k < n): the rows
-        dst's children of layer k+1 read through prefix modes; merged per slab"""
+        """[(src_lo, dst_lo, length)] element slices of layer k (k0 <= k < n) that ``src`` sends to ``dst`` after computing it,
+        in the compact coordinates of either rank: the rows dst's children of layer k+1 read through prefix modes"""
         L = self.layout
         out = []
+        so, do = self.offsets(k, src), self.offsets(k, dst)
         for w in sorted(self.halo[dst].keys()):
-            if w - 1 > k or w > k + 1:
+            if w > k + 1:
                 continue
             S = L.S[k][w - 1]
             for s_, lo, hi in self.halo[dst][w]:
                 if s_ == src:
-                    out.append((L.off[k][w - 1] + lo * S, L.off[k][w - 1] + hi * S))
+                    out.append((so[w - 1] + lo * S, do[w - 1] + lo * S, (hi - lo) * S))
         return out
 
     def recv_elems(self, q: int, k: int | None = None) -> int:
         ks = [k] if k is not None else range(self.k0, self.n)
-        return sum(hi - lo for kk in ks for s_ in range(self.world) for lo, hi in self.transfers(kk, s_, q))
+        return sum(ln for kk in ks for s_ in range(self.world) for _, _, ln in self.transfers(kk, s_, q))
 
     def send_elems(self, q: int, k: int | None = None) -> int:
         ks = [k] if k is not None else range(self.k0, self.n)
-        return sum(hi - lo for kk in ks for d in range(self.world) for lo, hi in self.transfers(kk, q, d))
+        return sum(ln for kk in ks for d in range(self.world) for _, _, ln in self.transfers(kk, q, d))
+
+    def buffer_elems(self, q: int):
+        """(A, B): complex elements of the two ping-pong layer buffers of rank q (layers n-1, n-3, .. in A; n-2, n-4, .. in B);
+        the replicated layers below k0 are held whole in rank order in the same buffers"""
+        n = self.n
+        size = {k: (self.storage(k, q)[1] if k >= self.k0 - 1 else self.count[k]) for k in range(0, n)}
+        size[self.k0 - 1] = max(size.get(self.k0 - 1, 1), self.count[self.k0 - 1])
+        a = max([size[k] for k in range(n - 1, -1, -2)] + [1])
+        b = max([size[k] for k in range(n - 2, -1, -2)] + [1])
+        return a, b
 
     def rho_ranges(self, k: int, q: int):
         """[(lo, hi)] per prefix weight w = 0..k: the prefixes of slab w that rank q computes at layer k ((0, 0): none)"""
@@ -204,10 +244,11 @@ class SlabChain:
       slab_fn(k, mk, parent_slab, rho_ranges, parent_off, child_off, child, probs, psum)
                                                                    this rank's prefixes of layer k, slab-major in and out
 
-    Layers k0-1 .. n-1 live in two full-size slab-major ping-pong buffers (global indexing: own parts are computed in place,
-    halos are received in place); the output probabilities are stored compactly, own slabs back to back (`out_slices`).
-    After layer k every rank sends, per consumer, the rows of its slabs that the consumer's children of layer k+1 read
-    through prefix modes: one NCCL send / recv group per layer, contiguous slices only.
+    Layers k0-1 .. n-1 live in two COMPACT slab-major ping-pong buffers (SlabPlan.storage: per slab the prefixes this rank owns
+    or reads, nothing else -- 14 photons / 28 modes needs 60 GB of the 192 GB layer 13 on the busiest of 8 ranks); the output
+    probabilities are stored compactly too, own slabs back to back (`out_slices`).  After layer k every rank sends, per
+    consumer, the rows of its slabs that the consumer's children of layer k+1 read through prefix modes: one NCCL
+    send / recv group per layer, contiguous slices only.
     """
 
     def __init__(self, plan: SlabPlan, order, alloc, alloc_real, full_fn, to_slab_fn, slab_fn, rank: int, group=None):
@@ -217,9 +258,9 @@ class SlabChain:
         n = plan.n
         self.n = n
         self.full_fn, self.to_slab_fn, self.slab_fn = full_fn, to_slab_fn, slab_fn
-        cnt = plan.count
-        self.buf_a = alloc(max(cnt[n - 1], 1))
-        self.buf_b = alloc(max(cnt[n - 2], 1) if n >= 2 else 1)
+        ea, eb = plan.buffer_elems(rank)
+        self.buf_a = alloc(ea)
+        self.buf_b = alloc(eb)
         # compact output: own slabs of layer n back to back; child_off[w] such that index = off + rho * S + t
         self.out_slices = []           # (w, rho_lo, rho_hi, offset, length)
         self.out_off = [0] * (n + 1)
@@ -233,11 +274,12 @@ class SlabChain:
         self.psum = torch.zeros(1, dtype=torch.float64, device=self.probs.device)
         self._xfer = {}
         for k in range(plan.k0, n):
-            sends = [(q, seg) for q in range(plan.world) for seg in plan.transfers(k, rank, q)]
-            recvs = [(q, seg) for q in range(plan.world) for seg in plan.transfers(k, q, rank)]
+            sends = [(q, lo, ln) for q in range(plan.world) for lo, _, ln in plan.transfers(k, rank, q)]
+            recvs = [(q, lo, ln) for q in range(plan.world) for _, lo, ln in plan.transfers(k, q, rank)]
             self._xfer[k] = (sends, recvs)
         self.bytes_received = 16 * plan.recv_elems(rank)
         self.bytes_sent = 16 * plan.send_elems(rank)
+        self.bytes = 16 * (ea + eb) + 8 * acc
 
     def _buf(self, k: int):
         return self.buf_a if (self.n - 1 - k) % 2 == 0 else self.buf_b
@@ -254,15 +296,14 @@ class SlabChain:
         if not sends and not recvs:
             return []
         flat = torch.view_as_real(buf)
-        ops = [dist.P2POp(dist.irecv, flat[lo:hi], q, self.group) for q, (lo, hi) in recvs]
-        ops += [dist.P2POp(dist.isend, flat[lo:hi], q, self.group) for q, (lo, hi) in sends]
+        ops = [dist.P2POp(dist.irecv, flat[lo:lo + ln], q, self.group) for q, lo, ln in recvs]
+        ops += [dist.P2POp(dist.isend, flat[lo:lo + ln], q, self.group) for q, lo, ln in sends]
         return dist.batch_isend_irecv(ops)
 
     def run(self, reduce_sum: bool = True, on_last=None):
         """one step: returns (compact probabilities of this rank's slabs, sum(p))"""
         import torch.distributed as dist
         plan, n, r = self.plan, self.n, self.rank
-        L = plan.layout
         cnt = plan.count
         self.psum.zero_()
         k0 = plan.k0
@@ -272,9 +313,8 @@ class SlabChain:
             buf = self._buf(k)
             self.full_fn(k, self.order[k - 1], parent, buf[:cnt[k]])
             parent = buf[:cnt[k]]
-        # layer k0-1 to slab-major (in the other buffer), then the sharded layers
         if k0 - 1 >= 1:
-            # permute through the other ping-pong buffer (free until layer k0 is written) and copy back in place
+            # layer k0-1 to slab-major: permute through the other ping-pong buffer (free until layer k0 is written)
             other = self._buf(k0)
             scratch = other[:cnt[k0 - 1]] if other.numel() >= cnt[k0 - 1] else self._scratch(cnt[k0 - 1])
             self.to_slab_fn(k0 - 1, parent, scratch)
@@ -288,15 +328,16 @@ class SlabChain:
             for w_ in works:
                 w_.wait()
             rr = plan.rho_ranges(k, r)
+            poff = plan.offsets(k - 1, r)
             if k < n:
                 buf = self._buf(k)
-                self.slab_fn(k, self.order[k - 1], parent, rr, L.off[k - 1], L.off[k], buf, None, None)
+                self.slab_fn(k, self.order[k - 1], parent, rr, poff, plan.offsets(k, r), buf, None, None)
                 works = self._exchange(k, buf)
                 parent = buf
             else:
                 if on_last is not None:
                     on_last("begin")
-                self.slab_fn(k, self.order[k - 1], parent, rr, L.off[k - 1], self.out_off, None, self.probs, self.psum)
+                self.slab_fn(k, self.order[k - 1], parent, rr, poff, self.out_off, None, self.probs, self.psum)
                 if on_last is not None:
                     on_last("end")
                 works = []

@@ -270,11 +270,17 @@ def _slab_worker(rank, world, port, outdir, m, in_state, shard_min):
         dst.index_copy_(0, torch.from_numpy(L.permutation(k)), src)
 
     def slab_fn(k, mk, parent, rr, poff, coff, child, probs, psum):
-        # emulate the slab kernel with the oracle: slab-major parent -> rank order (missing parents are NaN and poison exactly
-        # the children that read them), whole layer in rank order, then only this rank's prefixes are written
+        # emulate the slab kernel with the oracle: compact slab-major parent -> rank order (parents this rank does not hold,
+        # or never received, are NaN and poison exactly the children that read them), whole layer in rank order, then only
+        # this rank's prefixes are written
         perm_p, perm_c = L.permutation(k - 1), L.permutation(k)
-        parent_ro = parent.numpy()[:oracle.count(m, k - 1)][perm_p]
-        child_ro = gather_layer(k, mk, parent_ro)
+        parent_slab = np.full(oracle.count(m, k - 1), np.nan + 0j, dtype=np.complex128)
+        store, _size = plan.storage(k - 1, rank)
+        for w, (lo, hi, base) in enumerate(store):
+            S = L.S[k - 1][w]
+            assert poff[w] == base - lo * S
+            parent_slab[L.off[k - 1][w] + lo * S: L.off[k - 1][w] + hi * S] = parent.numpy()[base: base + (hi - lo) * S]
+        child_ro = gather_layer(k, mk, parent_slab[perm_p])
         child_slab = np.empty_like(child_ro)
         child_slab[perm_c] = child_ro
         states_slab = None
