@@ -272,7 +272,8 @@ class SLOSB200Backend(AStrongSimulationBackend):
             for st in root.states:                  # the vacuum input (n = 0): one state, coefficient 1
                 self._finish(st, 0, ranks0, vac, want_coefs[st])
             self._descend(root, [(ranks0, vac)], m, want_coefs)
-        eng.check_status()
+        if self._dev_mask is not None:
+            eng.check_status()      # synchronises; only the pruned kernels can flag an error (a kept child without its parent)
 
     def _descend(self, node: _PathNode, holder: list, m: int, want_coefs: dict):
         eng = self._eng()

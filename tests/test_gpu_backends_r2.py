@@ -90,7 +90,8 @@ def test_masked_run_is_pruned_and_equals_filtered_full_run(oracle, m, st, masks,
         assert abs(b.probability(BasicState([int(x) for x in s_])) - p) < 1e-13
     # pruning: every intermediate layer holds fewer states than the full layer, and the kept sets are nested correctly
     kept_sizes = {k: v.numel() for (k, budget), v in b._kept.items() if budget is not None}
-    assert kept_sizes and all(kept_sizes[k] < fsarray.count(m, k) for k in kept_sizes if k >= 2)
+    assert kept_sizes and all(kept_sizes[k] <= fsarray.count(m, k) for k in kept_sizes)
+    assert kept_sizes[n - 1] < fsarray.count(m, n - 1)      # the layer below the output is strictly pruned
     res = b._results[b._input_state]
     assert res.coefs.numel() == keep.sum() and res.ranks.numel() == keep.sum()
 
