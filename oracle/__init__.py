@@ -58,6 +58,7 @@ def lib():
         L.orc_slos_probs.argtypes = [i32, i32, vp, dbl, vp]
         L.orc_slos_amplitudes.argtypes = [i32, i32, vp, dbl, vp]
         L.orc_glynn_range.argtypes = [i32, vp, u64, u64, vp]
+        L.orc_glynn_range_ld.argtypes = [i32, vp, u64, u64, vp]
         L.orc_permanent.argtypes = [i32, vp, vp]
         L.orc_permanent_ryser.argtypes = [i32, vp, vp]
         L.orc_naive_submatrix.argtypes = [i32, i32, vp, vp, vp, vp]
@@ -197,6 +198,17 @@ def permanent(mat, g0: int | None = None, g1: int | None = None) -> complex:
         lib().orc_permanent(n, _p(mat), _p(out))
     else:
         lib().orc_glynn_range(n, _p(mat), g0, g1, _p(out))
+    return complex(out[0], out[1])
+
+
+def permanent_extended(mat, g0: int | None = None, g1: int | None = None) -> complex:
+    """The same Glynn walk in x87 extended precision (accuracy arbiter at n >= 28, rounded to double at the end)."""
+    mat = _u(mat)
+    n = mat.shape[0]
+    out = np.zeros(2)
+    if g0 is None:
+        g0, g1 = 0, 1 << max(n - 1, 0)
+    lib().orc_glynn_range_ld(n, _p(mat), g0, g1, _p(out))
     return complex(out[0], out[1])
 
 

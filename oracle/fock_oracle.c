@@ -305,16 +305,25 @@ void orc_slos_amplitudes(int m, int n, const double *coefs, double in_prodnfact,
  * walk over delta in {+-1}^n, delta_0 = +1:
  *   perm(M) = 2^{1-n} * sum_delta (prod_k delta_k) * prod_j ( sum_i delta_i M[i,j] )
  * Gray range [g0, g1) of the 2^{n-1} codes is exposed so the range split of SURVEY 8(e) can be checked. */
-static cplx glynn_range(int n, const cplx *M, uint64_t g0, uint64_t g1)
+/* The n column sums drift by one rounding per Gray step; over the millions of steps of a CPU chunk that drift (not the
+ * Kahan-compensated outer sum) would dominate the error of a permanent that is 1e7 times smaller than its terms (Haar
+ * sub-matrices at n = 30), so the sums are re-seeded exactly from the Gray code every ORC_RESEED steps. */
+#define ORC_RESEED 4096
+static void glynn_seed(int n, const cplx *M, uint64_t gray, cplx *v)
 {
-    cplx v[64];
-    /* delta for code g: bit b of gray(g) set => delta_{b+1} = -1 */
-    uint64_t gray = g0 ^ (g0 >> 1);
     for (int j = 0; j < n; ++j) {
         cplx acc = M[j]; /* row 0, delta_0 = +1 */
         for (int i = 1; i < n; ++i) acc += ((gray >> (i - 1)) & 1) ? -M[(size_t)i * n + j] : M[(size_t)i * n + j];
         v[j] = acc;
     }
+}
+
+static cplx glynn_range(int n, const cplx *M, uint64_t g0, uint64_t g1)
+{
+    cplx v[64];
+    /* delta for code g: bit b of gray(g) set => delta_{b+1} = -1 */
+    uint64_t gray = g0 ^ (g0 >> 1);
+    glynn_seed(n, M, gray, v);
     int sign = (__builtin_popcountll(gray) & 1) ? -1 : 1;
     cplx total = 0, comp = 0; /* Kahan on the outer sum */
     for (uint64_t g = g0; g < g1; ++g) {
@@ -327,18 +336,81 @@ static cplx glynn_range(int n, const cplx *M, uint64_t g0, uint64_t g1)
         /* next code: bit that flips between gray(g) and gray(g+1) = ctz(g+1) */
         uint64_t gn = g + 1;
         if (gn < g1) {
-            int b = __builtin_ctzll(gn);
             uint64_t ngray = gn ^ (gn >> 1);
-            int now_minus = (int)((ngray >> b) & 1);
-            const cplx *row = M + (size_t)(b + 1) * n;
-            if (now_minus)
-                for (int j = 0; j < n; ++j) v[j] -= 2.0 * row[j];
-            else
-                for (int j = 0; j < n; ++j) v[j] += 2.0 * row[j];
+            if ((gn & (ORC_RESEED - 1)) == 0) {
+                glynn_seed(n, M, ngray, v);
+            } else {
+                int b = __builtin_ctzll(gn);
+                int now_minus = (int)((ngray >> b) & 1);
+                const cplx *row = M + (size_t)(b + 1) * n;
+                if (now_minus)
+                    for (int j = 0; j < n; ++j) v[j] -= 2.0 * row[j];
+                else
+                    for (int j = 0; j < n; ++j) v[j] += 2.0 * row[j];
+            }
             sign = -sign;
         }
     }
     return total;
+}
+
+/* The same walk in x87 extended precision (64-bit mantissa): the accuracy arbiter between this oracle and the device
+ * kernels at the sizes where a double-precision Glynn sum is within a few units of the 1e-10 tolerance (n >= 28). */
+typedef long double _Complex lcplx;
+static lcplx glynn_range_ld(int n, const cplx *M, uint64_t g0, uint64_t g1)
+{
+    lcplx v[64];
+    uint64_t gray = g0 ^ (g0 >> 1);
+    int sign = (__builtin_popcountll(gray) & 1) ? -1 : 1;
+    lcplx total = 0;
+    for (uint64_t g = g0; g < g1; ++g) {
+        if (g == g0 || (g & (ORC_RESEED - 1)) == 0) {
+            uint64_t gr = g ^ (g >> 1);
+            for (int j = 0; j < n; ++j) {
+                lcplx acc = (lcplx)M[j];
+                for (int i = 1; i < n; ++i) acc += ((gr >> (i - 1)) & 1) ? -(lcplx)M[(size_t)i * n + j] : (lcplx)M[(size_t)i * n + j];
+                v[j] = acc;
+            }
+        }
+        lcplx prod = v[0];
+        for (int j = 1; j < n; ++j) prod *= v[j];
+        total += (sign > 0 ? prod : -prod);
+        uint64_t gn = g + 1;
+        if (gn < g1 && (gn & (ORC_RESEED - 1)) != 0) {
+            int b = __builtin_ctzll(gn);
+            uint64_t ngray = gn ^ (gn >> 1);
+            const cplx *row = M + (size_t)(b + 1) * n;
+            if ((ngray >> b) & 1)
+                for (int j = 0; j < n; ++j) v[j] -= 2.0L * (lcplx)row[j];
+            else
+                for (int j = 0; j < n; ++j) v[j] += 2.0L * (lcplx)row[j];
+        }
+        sign = -sign;
+    }
+    return total;
+}
+
+void orc_glynn_range_ld(int n, const double *mat, uint64_t g0, uint64_t g1, double *out)
+{
+    const cplx *M = (const cplx *)mat;
+    if (n == 0) { out[0] = 1; out[1] = 0; return; }
+    long double sr = 0, si = 0;
+    uint64_t tot = g1 - g0;
+    int chunks = 1;
+#ifdef _OPENMP
+    chunks = omp_get_max_threads() * 8;
+#endif
+    if ((uint64_t)chunks > tot) chunks = (int)(tot ? tot : 1);
+#pragma omp parallel for schedule(dynamic) reduction(+ : sr, si)
+    for (int c = 0; c < chunks; ++c) {
+        uint64_t lo = g0 + tot * (uint64_t)c / (uint64_t)chunks, hi = g0 + tot * (uint64_t)(c + 1) / (uint64_t)chunks;
+        lcplx r = glynn_range_ld(n, M, lo, hi);
+        sr += creall(r);
+        si += cimagl(r);
+    }
+    long double scale = ldexpl(1.0L, 1 - n);
+    out[0] = (double)(sr * scale);
+    out[1] = (double)(si * scale);
 }
 
 /* out = [re, im].  Threaded over Gray chunks. */

@@ -415,9 +415,11 @@ def test_large_probability_layer_default_kernel_sharded(eng, oracle):
 @pytest.mark.parametrize("n,frac", [(25, 1), (28, 1), (30, 1), (31, 2), (32, 4)])
 def test_glynn_big_kernel_headline_sizes_vs_oracle(eng, oracle, n, frac):
     """glynn_big_kernel<n> at the sizes BASELINE.json names (reference perceval/backends/_naive.py:70-71): one Haar
-    sub-matrix per n.  n <= 30: the whole permanent against the oracle (8 s of OpenMP at n = 30); n >= 31: 1/frac of the Gray range, taken as three
-    sub-ranges (start, an unaligned middle piece, the end), each against the oracle's partial sum over the same codes,
-    plus the whole permanent against the sum of the device's own quarters (additivity over the Gray range)."""
+    sub-matrix per n (its permanent is ~1e7 times smaller than the terms of the Glynn sum, so 1e-10 relative is within two
+    orders of what double precision can deliver at all).  n <= 28: device and oracle against the oracle's extended-precision
+    walk (the arbiter); n = 30: the whole permanent against the oracle; n >= 31: 1/frac of the Gray range, taken as three
+    sub-ranges (start, an unaligned middle piece, the end), each against the oracle's partial sum over the same codes, plus
+    the whole permanent against the sum of the device's own quarters (additivity over the Gray range)."""
     u = oracle.random_unitary(2 * n, seed=n)
     mat = np.ascontiguousarray(u[:n, :n])
     M = torch.from_numpy(mat[None])
@@ -425,6 +427,10 @@ def test_glynn_big_kernel_headline_sizes_vs_oracle(eng, oracle, n, frac):
     if frac == 1:
         got = complex(eng.permanents(M).cpu().numpy()[0])
         ref = oracle.permanent(mat)
+        if n <= 28:
+            exact = oracle.permanent_extended(mat)
+            assert abs(ref - exact) <= REL * abs(exact), (n, ref, exact)
+            assert abs(got - exact) <= REL * abs(exact), (n, got, exact)
         assert abs(got - ref) <= REL * abs(ref), (n, got, ref)
         return
     piece = G // (3 * frac)
@@ -433,6 +439,7 @@ def test_glynn_big_kernel_headline_sizes_vs_oracle(eng, oracle, n, frac):
         got = complex(eng.permanents(M, g0, g0 + piece).cpu().numpy()[0])
         ref = oracle.permanent(mat, g0, g0 + piece)
         scale = max(scale, abs(ref))
+        # a partial sum is not small compared with its terms: the tolerance is relative to the partial sum itself
         assert abs(got - ref) <= REL * abs(ref), (n, g0, got, ref)
     whole = complex(eng.permanents(M).cpu().numpy()[0])
     quarters = sum(complex(eng.permanents(M, q * (G // 4), (q + 1) * (G // 4)).cpu().numpy()[0]) for q in range(4))

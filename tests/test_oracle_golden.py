@@ -244,3 +244,17 @@ def test_slos_order(oracle):
     assert oracle.slos_order((2, 1, 0)) == [0, 0, 1]
     assert oracle.slos_order((0, 3, 1)) == [1, 1, 1, 2]
     assert oracle.slos_order((1, 2)) == [1, 0, 1]
+
+
+def test_glynn_double_vs_extended_precision(oracle):
+    """The oracle's double-precision Glynn walk (Kahan sum, column sums re-seeded every 4096 codes) against the same walk in
+    x87 extended precision, on Haar sub-matrices whose permanent is orders of magnitude smaller than the terms of the sum."""
+    import numpy as np
+    for n in (8, 16, 22, 24):
+        u = oracle.random_unitary(2 * n, seed=n)
+        mat = np.ascontiguousarray(u[:n, :n])
+        a, b = oracle.permanent(mat), oracle.permanent_extended(mat)
+        assert abs(a - b) <= 2e-11 * abs(b), (n, a, b)
+        G = 1 << (n - 1)
+        parts = sum(oracle.permanent_extended(mat, q * (G // 4), (q + 1) * (G // 4)) for q in range(4))
+        assert abs(parts - b) <= 1e-12 * abs(b)
