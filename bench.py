@@ -195,7 +195,7 @@ def perm_flops(nn: int) -> float:
 
 
 def run_reference_permanents(args, oracle, cores):
-    nn, B = args.n, 1
+    nn, B = args.perm_n, 1
     mats = haar_submatrices(nn, B)
     G = 1 << (nn - 1)
     frac = 1
@@ -655,7 +655,7 @@ def run_permanents(args, torch, dist, world, rank, local_rank, barrier, rmax):
     from perceval_b200 import dist as pdist
     from perceval_b200.engine import FockEngine
     eng = FockEngine.get(local_rank)
-    nn, B = args.n, args.batch
+    nn, B = args.perm_n, args.batch
     mats_h = torch.from_numpy(haar_submatrices(nn, B)).pin_memory()
     mats = mats_h.to(eng.device)
     fp64 = measure_fp64(eng)
@@ -845,7 +845,7 @@ def main():
     ap.add_argument("--workload", default="slos", choices=["slos", "permanents", "cc2017"])
     ap.add_argument("--photons", type=int, default=N_PHOTONS)
     ap.add_argument("--modes", type=int, default=N_MODES)
-    ap.add_argument("--n", type=int, default=30, help="permanents: matrix size")
+    ap.add_argument("--perm-n", type=int, default=30, help="permanents: matrix size (torchrun's own parser swallows a bare --n)")
     ap.add_argument("--batch", type=int, default=8, help="permanents: matrices per step (whole job)")
     ap.add_argument("--samples", type=int, default=100000, help="cc2017: samples per step (whole job)")
     ap.add_argument("--e2e-pieces", type=int, default=8)

@@ -68,8 +68,8 @@ def load():
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB
-            if not os.path.exists(path) or os.environ.get("FOCK_B200_REBUILD"):
+            path = os.environ.get("FOCK_B200_LIB") or _build.LIB     # FOCK_B200_LIB: a tuning build (tools/build_variant.py)
+            if path == _build.LIB and (not os.path.exists(path) or os.environ.get("FOCK_B200_REBUILD")):
                 _build.build()
             L = C.CDLL(path)
             for name, res, args in SYMBOLS:

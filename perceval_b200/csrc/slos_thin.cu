@@ -78,6 +78,23 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl
     const uint32_t t16 = t << 4;
     const uint32_t *col = sh.s_col + tid;
     const uint32_t s_utrail = (uint32_t)__cvta_generic_to_shared(sh.s_u + p + TH6_LEAD);
+#ifdef TH6_REGCOL
+    // tuning variant (tools/build_variant.py): the slot offsets and the tail factorial in registers instead of one LDS per slot
+    // and sweep step -- needs a larger register budget (TH_MINB = 3)
+    uint32_t rcl[WL], rct[WT];
+#pragma unroll
+    for (int s = 0; s < WL; ++s) rcl[s] = col[s * TILE_BLOCK];
+#pragma unroll
+    for (int c = 0; c < WT; ++c) rct[c] = col[(TH6_LEAD + c) * TILE_BLOCK];
+    const double tfreg = __hiloint2double((int)col[(D + 1) * TILE_BLOCK], (int)col[D * TILE_BLOCK]);
+#define TH6_COLL(s) rcl[s]
+#define TH6_COLT(c) rct[c]
+#define TH6_TF tfreg
+#else
+#define TH6_COLL(s) col[(s) * TILE_BLOCK]
+#define TH6_COLT(c) col[(TH6_LEAD + (c)) * TILE_BLOCK]
+#define TH6_TF __hiloint2double((int)col[(D + 1) * TILE_BLOCK], (int)col[D * TILE_BLOCK])
+#endif
     for (uint64_t rho0 = rho_a; rho0 < rho_b; rho0 += TH_DB) {
         const int nb = (int)((rho_b - rho0) < (uint64_t)TH_DB ? (rho_b - rho0) : (uint64_t)TH_DB);
         th_bar();
@@ -149,7 +166,7 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl
 #pragma unroll
             for (int s = 0; s < 4 && s < WL; ++s) {
                 tv[s] = make_double2(0.0, 0.0);
-                if (pm & (1u << s)) tv[s] = th_ldg(td.tptr + col[s * TILE_BLOCK]);
+                if (pm & (1u << s)) tv[s] = th_ldg(td.tptr + TH6_COLL(s));
             }
             double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
@@ -167,7 +184,7 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl
 #pragma unroll
                 for (int s = 4; s < WL; ++s) {
                     tv[s - 4] = make_double2(0.0, 0.0);
-                    if (pm & (1u << s)) tv[s - 4] = th_ldg(td.tptr + col[s * TILE_BLOCK]);
+                    if (pm & (1u << s)) tv[s - 4] = th_ldg(td.tptr + TH6_COLL(s));
                 }
 #pragma unroll
                 for (int s = 4; s < WL; ++s) acc = cfma(c_th_u[a.uslot][p + ((wm_lo >> (4 * s)) & 15u)], tv[s - 4], acc);
@@ -181,7 +198,7 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl
                     x[c - c0] = 0;
                     tv[c - c0] = make_double2(0.0, 0.0);
                     if (pm & (1u << (TH6_LEAD + c))) {
-                        x[c - c0] = col[(TH6_LEAD + c) * TILE_BLOCK];
+                        x[c - c0] = TH6_COLT(c);
                         tv[c - c0] = th_ldg(td.tptr + (x[c - c0] & ~15u));
                     }
                 }
@@ -194,8 +211,7 @@ __device__ __forceinline__ void th6_sweep(const TileArgs &a, const TileClass &cl
             }
             if (MODE & 1) a.child[r - a.cbegin] = acc;
             if (MODE & 2) {
-                const double tf = __hiloint2double((int)col[(D + 1) * TILE_BLOCK], (int)col[D * TILE_BLOCK]);
-                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * tf);
+                const double pr = (acc.x * acc.x + acc.y * acc.y) * a.inv_in_fact * (td.pfact * TH6_TF);
                 __stcs(a.probs + (r - a.cbegin), pr);
                 local_sum += pr;
             }

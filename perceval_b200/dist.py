@@ -511,7 +511,7 @@ class ExchangeChain:
         return self.probs, (self.begin, self.end), self.psum
 
 
-def engine_exchange_chain(engine, U_ref, in_state, group=None, pieces: int = 4, shard_min: int = 1 << 23, boundaries=None):
+def engine_exchange_chain(engine, U_ref, in_state, group=None, pieces: int = 4, shard_min: int = 1 << 23, fractions=None):
     """Device instantiation of ExchangeChain: kernels from libfock_b200.so, NCCL send / recv over NVLink.  ``U_ref`` is a
     one-element list holding the device unitary, so that a step can swap it without rebuilding plan and buffers."""
     from .engine import prodnfact
@@ -520,7 +520,7 @@ def engine_exchange_chain(engine, U_ref, in_state, group=None, pieces: int = 4, 
     _rank, world = _world(group)
     order = engine.slos_order(occ)
     inf = prodnfact(occ)
-    plan = ExchangePlan(m, n, world, pieces=pieces, shard_min=shard_min, boundaries=boundaries)
+    plan = ExchangePlan(m, n, world, pieces=pieces, shard_min=shard_min, fractions=fractions)
     vac = torch.ones(1, dtype=torch.complex128, device=engine.device)
 
     def alloc(k):

@@ -12,7 +12,7 @@ prefix-mode parents from the aligned rows (w-1, rho', t), rho' = rank of (prefix
 (reference perceval/backends/_slos.py:91-97 read as a gather; kernels: slos_layer_slab in csrc/slos.cu).
 
 Ownership.  Rank q owns a contiguous run of prefixes in slab-major order (w ascending, rho ascending), THE SAME for every
-layer, cut so that the output layer is balanced.  Tail-mode parents are therefore always local; what crosses NVLink are
+layer, cut so that the states of all sharded layers together are balanced.  Tail-mode parents are therefore always local; what crosses NVLink are
 prefix-mode rows only: for every owned (w, [a, b)) the rho' window of slab w-1 (partition.parent_segments on the prefix
 space FS(p, w), exact) minus what the rank owns itself -- contiguous slices of the neighbours' slabs.  At 12 photons /
 24 modes on 8 GPUs a rank receives 1.0 GB for the output layer instead of the 1.6 - 3.0 GB of rank-contiguous ranges, every
@@ -108,12 +108,15 @@ class SlabPlan:
                 k0 = k
                 break
         self.k0 = max(1, min(k0, n))
-        # contiguous runs of prefixes balanced on the output layer; own[q] = [(w, a, b)] with whole prefixes
-        total = cnt[n]
+        # contiguous runs of whole prefixes, own[q] = [(w, a, b)], balanced on the states a prefix contributes to ALL the sharded
+        # layers (a state costs about the same 15 - 16 ps in every layer: profiles/README.md), so that no rank is the slowest on
+        # layer n-1 because it was balanced for layer n only
+        cost = [sum(L.S[k][w] for k in range(max(self.k0, w), n + 1)) for w in range(n + 1)]
+        total = sum(L.nprefix[w] * cost[w] for w in range(n + 1))
         self.own = [[] for _ in range(world)]
         cum, q = 0, 0
         for w in range(n + 1):
-            sw, a = L.S[n][w], 0
+            sw, a = cost[w], 0
             while a < L.nprefix[w]:
                 room = total * (q + 1) // world - cum
                 take = min(L.nprefix[w] - a, max(1, -(-room // sw))) if (room > 0 or q == world - 1) else 0
@@ -325,21 +328,32 @@ class SlabChain:
             parent[:1] = 1.0               # the vacuum: one prefix of weight 0, one tail
         works = []
         for k in range(k0, n + 1):
-            for w_ in works:
-                w_.wait()
             rr = plan.rho_ranges(k, r)
             poff = plan.offsets(k - 1, r)
+            # slabs whose prefix rows are all local run first, while the rows of the others are still on the wire
+            free = [(lo, hi) if not plan.halo[r].get(w) else (0, 0) for w, (lo, hi) in enumerate(rr)]
+            rest = [(lo, hi) if plan.halo[r].get(w) else (0, 0) for w, (lo, hi) in enumerate(rr)]
+            parts = [p_ for p_ in (free, rest) if any(hi > lo for lo, hi in p_)] if works else [rr]
+            for part in parts:
+                if part is rest:
+                    for w_ in works:
+                        w_.wait()
+                    works = []
+                if k < n:
+                    self.slab_fn(k, self.order[k - 1], parent, part, poff, plan.offsets(k, r), self._buf(k), None, None)
+                else:
+                    if on_last is not None:
+                        on_last("begin")
+                    self.slab_fn(k, self.order[k - 1], parent, part, poff, self.out_off, None, self.probs, self.psum)
+                    if on_last is not None:
+                        on_last("end")
+            for w_ in works:           # sends of layer k-1 read the buffer that layer k+1 is about to overwrite
+                w_.wait()
             if k < n:
                 buf = self._buf(k)
-                self.slab_fn(k, self.order[k - 1], parent, rr, poff, plan.offsets(k, r), buf, None, None)
                 works = self._exchange(k, buf)
                 parent = buf
             else:
-                if on_last is not None:
-                    on_last("begin")
-                self.slab_fn(k, self.order[k - 1], parent, rr, poff, self.out_off, None, self.probs, self.psum)
-                if on_last is not None:
-                    on_last("end")
                 works = []
         if reduce_sum and plan.world > 1:
             dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
