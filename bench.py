@@ -295,7 +295,11 @@ def dist_setup():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        try:    # NCCL's copy kernels on a high-priority stream: a halo transfer must not queue behind a 130 000-CTA compute grid
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         if world > 1:
@@ -527,9 +531,19 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
             else:
                 events[-1][1] = evt
 
+        marks = []
+
+        def mark(label):
+            evt = torch.cuda.Event(enable_timing=True)
+            evt.record()
+            marks.append((label, evt))
+
         def step(Udev=U):
             U_ref[0] = Udev
-            chain.run(reduce_sum=False, on_last=on_last)
+            marks.clear()
+            if args.timeline:
+                mark("start")
+            chain.run(reduce_sum=False, on_last=on_last, mark=mark if args.timeline else None)
         Lh = plan.layout
         rows_last = sum((hi - lo) * Lh.S[n - 1][w - 1] for w, segs in plan.rows[rank].items() for lo, hi in segs)
         tails_last = sum((bb - aa) * Lh.S[n - 1][w] for w, aa, bb in plan.own[rank] if w <= n - 1)
@@ -627,6 +641,13 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
             "data": "synthetic", "config": slos_config(n, m, N, partition=desc, partition_name=partition),
             "roofline": roofline, "nvlink": nvlink, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "sum_p": total_p,
             "spot_check": {"outputs_per_rank": args.spot, "against": "oracle.naive_amplitude (CPU permanents)", "worst_rel_err": worst}}
+    if args.timeline and partition == "slab":
+        step()
+        torch.cuda.synchronize()
+        tl = [(marks[i + 1][0], round(marks[i][1].elapsed_time(marks[i + 1][1]), 3)) for i in range(len(marks) - 1)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, tl)
+        line["timeline_ms_per_rank"] = gathered
     if rank == 0:
         print(json.dumps(line), flush=True)
 
@@ -858,6 +879,7 @@ def main():
     ap.add_argument("--sub", type=int, default=0, help="windowed: sub-shards per rank (0 = from free memory)")
     ap.add_argument("--spot", type=int, default=64, help="outputs (per rank) checked against the CPU oracle outside the timed region")
     ap.add_argument("--reference-budget-s", type=float, default=240.0)
+    ap.add_argument("--timeline", action="store_true", help="slab partition: per-rank time of every phase of one step (CUDA events)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -42,8 +42,11 @@ struct CcArgs {
     uint8_t *out;       // count x m
 };
 
+#ifndef CC_MINB
+#define CC_MINB 1   // tuning knob (tools/build_variant.py): minimum CTAs per SM the register allocation must allow
+#endif
 template <int H>
-__global__ void __launch_bounds__(CC_BLOCK) cc2017_kernel(const CcArgs a) {
+__global__ void __launch_bounds__(CC_BLOCK, CC_MINB) cc2017_kernel(const CcArgs a) {
     constexpr int NP = 4 * H;  // padded column count
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.m, n = a.n;

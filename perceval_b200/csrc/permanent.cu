@@ -87,8 +87,11 @@ __device__ __forceinline__ double2 glynn_chunk(const double2 *__restrict__ M, ui
 }
 
 // one matrix per blockIdx.y (looped), Gray chunks over blockIdx.x * GLYNN_BLOCK threads
+#ifndef GLYNN_MINB
+#define GLYNN_MINB 1   // tuning knob (tools/build_variant.py): minimum CTAs per SM the register allocation must allow
+#endif
 template <int N>
-__global__ void __launch_bounds__(GLYNN_BLOCK) glynn_big_kernel(const double2 *__restrict__ mats, uint64_t B, double2 *__restrict__ partials,
+__global__ void __launch_bounds__(GLYNN_BLOCK, GLYNN_MINB) glynn_big_kernel(const double2 *__restrict__ mats, uint64_t B, double2 *__restrict__ partials,
                                                                 uint64_t gbegin, uint64_t gend, int chunk_log2) {
     __shared__ double2 sM[N * N];
     __shared__ double2 s_red[GLYNN_BLOCK / 32];

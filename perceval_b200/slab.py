@@ -303,10 +303,13 @@ class SlabChain:
         ops += [dist.P2POp(dist.isend, flat[lo:lo + ln], q, self.group) for q, lo, ln in sends]
         return dist.batch_isend_irecv(ops)
 
-    def run(self, reduce_sum: bool = True, on_last=None):
-        """one step: returns (compact probabilities of this rank's slabs, sum(p))"""
+    def run(self, reduce_sum: bool = True, on_last=None, mark=None):
+        """one step: returns (compact probabilities of this rank's slabs, sum(p)).  ``mark(label)`` is called at the phase
+        boundaries of the step (replicated layers, each layer's launches, each wait for a halo) -- bench.py records a CUDA
+        event there to print where a step spends its time."""
         import torch.distributed as dist
         plan, n, r = self.plan, self.n, self.rank
+        mark = mark or (lambda label: None)
         cnt = plan.count
         self.psum.zero_()
         k0 = plan.k0
@@ -327,6 +330,7 @@ class SlabChain:
             parent = self._buf(0)
             parent[:1] = 1.0               # the vacuum: one prefix of weight 0, one tail
         works = []
+        mark("replicated")
         for k in range(k0, n + 1):
             rr = plan.rho_ranges(k, r)
             poff = plan.offsets(k - 1, r)
@@ -339,6 +343,7 @@ class SlabChain:
                     for w_ in works:
                         w_.wait()
                     works = []
+                    mark(f"wait{k}")
                 if k < n:
                     self.slab_fn(k, self.order[k - 1], parent, part, poff, plan.offsets(k, r), self._buf(k), None, None)
                 else:
@@ -347,6 +352,7 @@ class SlabChain:
                     self.slab_fn(k, self.order[k - 1], parent, part, poff, self.out_off, None, self.probs, self.psum)
                     if on_last is not None:
                         on_last("end")
+            mark(f"layer{k}")
             for w_ in works:           # sends of layer k-1 read the buffer that layer k+1 is about to overwrite
                 w_.wait()
             if k < n:
