@@ -108,10 +108,13 @@ class SlabPlan:
                 k0 = k
                 break
         self.k0 = max(1, min(k0, n))
-        # contiguous runs of whole prefixes, own[q] = [(w, a, b)], balanced on the states a prefix contributes to ALL the sharded
-        # layers (a state costs about the same 15 - 16 ps in every layer: profiles/README.md), so that no rank is the slowest on
-        # layer n-1 because it was balanced for layer n only
-        cost = [sum(L.S[k][w] for k in range(max(self.k0, w), n + 1)) for w in range(n + 1)]
+        # contiguous runs of whole prefixes, own[q] = [(w, a, b)], balanced on the modelled time a prefix costs over ALL the sharded
+        # layers.  A child costs c + s / (prefixes its CTA sweeps): every thread sets its tail up once per sweep, and the slabs
+        # with few prefixes (w = 0: one prefix, 2 % of the states of 12/24) amortise that over little work.  c = 12.2 ps,
+        # s = 61 ps fitted to the measured single-GPU layer (14.6 ps per state) and to a rank that held only w <= 2 (21 ps).
+        def per_state(w):
+            return 12.2 + 61.0 / min(max(L.nprefix[w], 1), 128)
+        cost = [int(1000 * per_state(w)) * sum(L.S[k][w] for k in range(max(self.k0, w), n + 1)) for w in range(n + 1)]
         total = sum(L.nprefix[w] * cost[w] for w in range(n + 1))
         self.own = [[] for _ in range(world)]
         cum, q = 0, 0
