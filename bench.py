@@ -517,7 +517,7 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     elif partition == "slab":
         from perceval_b200 import slab as pslab
         U_ref = [U]
-        chain = pslab.engine_slab_chain(eng, U_ref, in_state, shard_min=args.shard_min)
+        chain = pslab.engine_slab_chain(eng, U_ref, in_state, shard_min=args.shard_min, pieces=args.pieces)
         plan = chain.plan
         b, e = 0, chain.probs.numel()          # compact slab-major storage of this rank's prefixes (chain.out_slices)
         get_probs = lambda: chain.probs
@@ -662,6 +662,9 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     e2e = {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": int(u_host.numel() * 16), "d2h_bytes_per_step": int((e - b) * 8),
            "api": "per rank: U.copy_(pinned host U) + the partition's chain + this rank's probabilities to the host through a 2 x 256 MB pinned ring (consumed = summed on the host)"}
+    nvlink = {"bytes_received_per_step_this_rank": nvlink["bytes_received_per_step"], "bytes_sent_per_step_this_rank": nvlink["bytes_sent_per_step"],
+              "bytes_received_per_step_max_rank": int(rmax(nvlink["bytes_received_per_step"])),
+              "bytes_sent_per_step_max_rank": int(rmax(nvlink["bytes_sent_per_step"]))}
     line = {"metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128",
             "data": "synthetic", "config": slos_config(n, m, N, partition=desc, partition_name=partition),
@@ -900,7 +903,7 @@ def main():
                     help="N > 1: slab = prefix slabs owned by rank, prefix rows over NVLink (default when two whole layers fit); "
                          "replicate = lower layers on every rank, output layer sharded by rank range; exchange = rank ranges + NVLink "
                          "halo exchange; windowed = recompute-window chain (no exchange, the only one that fits 14/28)")
-    ap.add_argument("--pieces", type=int, default=4, help="exchange: child pieces / exchange groups per layer")
+    ap.add_argument("--pieces", type=int, default=4, help="slab / exchange: pieces per rank and layer = exchange groups per layer")
     ap.add_argument("--shard-min", type=int, default=1 << 23, help="exchange: layers with fewer states are replicated")
     ap.add_argument("--sub", type=int, default=0, help="windowed: sub-shards per rank (0 = from free memory)")
     ap.add_argument("--spot", type=int, default=64, help="outputs (per rank) checked against the CPU oracle outside the timed region")

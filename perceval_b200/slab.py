@@ -82,6 +82,26 @@ class SlabLayout:
         return self._cache[key]
 
 
+def _subtract(segs, seen):
+    """parts of the half-open ranges ``segs`` not covered by the sorted, merged ranges ``seen``"""
+    out = []
+    for lo, hi in segs:
+        cur = lo
+        for a, b in seen:
+            if b <= cur:
+                continue
+            if a >= hi:
+                break
+            if a > cur:
+                out.append((cur, a))
+            cur = max(cur, b)
+            if cur >= hi:
+                break
+        if cur < hi:
+            out.append((cur, hi))
+    return out
+
+
 def _prefixes_desc(p: int, kmax: int):
     """all prefixes of p modes with at most kmax photons, in the order they appear in FSArray(m, k) (descending lex)"""
     def rec(i, left):
@@ -97,7 +117,7 @@ def _prefixes_desc(p: int, kmax: int):
 class SlabPlan:
     """Ownership + halo lists, identical on every rank (pure integer arithmetic)."""
 
-    def __init__(self, m: int, n: int, world: int, shard_min: int = 1 << 23):
+    def __init__(self, m: int, n: int, world: int, shard_min: int = 1 << 23, pieces: int = 4):
         self.layout = L = SlabLayout(m, n)
         self.m, self.n, self.world = m, n, world
         cnt = [P.count(m, k) for k in range(n + 1)]
@@ -145,24 +165,71 @@ class SlabPlan:
         for q in range(world):
             for w, a, b in self.own[q]:
                 self._owners.setdefault(w, []).append((q, a, b))
-        # halo[q][w] = [(src, lo, hi)]: rho' ranges of slab w-1 that rank q reads through prefix modes but does not own
-        self.rows = [{} for _ in range(world)]      # rows[q][w] = merged rho' segments of slab w-1 needed by q's part of slab w
-        self.halo = [{} for _ in range(world)]
+        # rows[q][w] = merged rho' segments of slab w-1 that q's part of slab w reads through prefix modes (owned or not)
+        self.rows = [{} for _ in range(world)]
         for q in range(world):
             for w, a, b in self.own[q]:
-                if w == 0:
-                    continue
-                segs = P.parent_segments(L.p, w, [(a, b)], max_segments=4)
-                self.rows[q][w] = segs
-                need = []
-                for lo, hi in segs:
-                    for src, sa, sb in self._owners.get(w - 1, []):
-                        if src == q:
-                            continue
-                        x, y = max(lo, sa), min(hi, sb)
-                        if y > x:
-                            need.append((src, x, y))
-                self.halo[q][w] = need
+                if w >= 1:
+                    self.rows[q][w] = P.parent_segments(L.p, w, [(a, b)], max_segments=4)
+        # PIECES.  A rank's prefixes are cut into about ``pieces`` runs of equal modelled cost, computed one launch after the
+        # other; the exchange that follows a layer is cut into as many GROUPS, group g carrying the rows piece g of the next
+        # layer reads that no earlier piece needed and the rank does not own.  Piece g starts when group g has arrived, while the
+        # later groups are still on the wire.  Pieces whose rows are all local come first (they never wait).  With 12 prefix
+        # modes (14 photons / 28 modes) the windows of consecutive pieces are almost disjoint, so the transfer of a layer
+        # hides behind its own computation; with 8 (12/24) the first piece needs 60 - 80 % of the halo and little is hidden.
+        self.piece = [[] for _ in range(world)]         # piece[q][g] = [(w, a, b)]
+        self.fresh = [[] for _ in range(world)]         # fresh[q][g] = [(src, w-1, lo, hi)] rows to receive before piece g
+        for q in range(world):
+            mine = sum((b - a) * cost[w] for w, a, b in self.own[q])
+            target = max(1, -(-mine // max(1, pieces)))
+            cur, acc, out = [], 0, []
+            for w, a, b in self.own[q]:
+                while a < b:
+                    room = target - acc
+                    take = min(b - a, max(1, room // max(cost[w], 1)))
+                    if cur and cur[-1][0] == w and cur[-1][2] == a:
+                        cur[-1] = (w, cur[-1][1], a + take)
+                    else:
+                        cur.append((w, a, a + take))
+                    acc += take * cost[w]
+                    a += take
+                    if acc >= target:
+                        out.append(cur)
+                        cur, acc = [], 0
+            if cur:
+                out.append(cur)
+            need = []
+            for pc in out:
+                rows = []
+                for w, a, b in pc:
+                    if w >= 1:
+                        for lo, hi in P.parent_segments(L.p, w, [(a, b)], max_segments=4):
+                            for src, sa, sb in self._owners.get(w - 1, []):
+                                if src != q:
+                                    x, y = max(lo, sa), min(hi, sb)
+                                    if y > x:
+                                        rows.append((src, w - 1, x, y))
+                need.append(rows)
+            # processing order: greedily the piece whose rows add the least to what has already been received (pieces with
+            # local rows only come first; windows that nest -- the late prefixes of a slab read a subset of what the early ones
+            # read -- are walked from the inside out, so every group carries about the same volume)
+            def volume(rows, seen):
+                return sum((y - x) * L.S[n - 1][wp] if wp <= n - 1 else 0
+                           for src, wp, lo, hi in rows for x, y in _subtract([(lo, hi)], seen.get((src, wp), [])))
+            seen, left = {}, list(range(len(out)))
+            while left:
+                i = min(left, key=lambda j: (volume(need[j], seen), j))
+                left.remove(i)
+                fr = []
+                for src, wp, lo, hi in need[i]:
+                    for x, y in _subtract([(lo, hi)], seen.get((src, wp), [])):
+                        fr.append((src, wp, x, y))
+                    seen[(src, wp)] = P.merge_segments(seen.get((src, wp), []) + [(lo, hi)], max_segments=1 << 30)
+                self.piece[q].append(out[i])
+                self.fresh[q].append(fr)
+
+    def groups(self) -> int:
+        return max(len(p_) for p_ in self.piece)
 
     def owner_ranges(self, w: int):
         return self._owners.get(w, [])
@@ -198,19 +265,20 @@ class SlabPlan:
         L = self.layout
         return [base - lo * L.S[k][w] for w, (lo, hi, base) in enumerate(self.storage(k, q)[0])]
 
-    def transfers(self, k: int, src: int, dst: int):
+    def transfers(self, k: int, src: int, dst: int, g: int | None = None):
         """[(src_lo, dst_lo, length)] element slices of layer k (k0 <= k < n) that ``src`` sends to ``dst`` after computing it,
-        in the compact coordinates of either rank: the rows dst's children of layer k+1 read through prefix modes"""
+        in the compact coordinates of either rank: the rows dst's children of layer k+1 read through prefix modes (of dst's
+        piece g only, if given)"""
         L = self.layout
         out = []
         so, do = self.offsets(k, src), self.offsets(k, dst)
-        for w in sorted(self.halo[dst].keys()):
-            if w > k + 1:
+        for gg, fr in enumerate(self.fresh[dst]):
+            if g is not None and gg != g:
                 continue
-            S = L.S[k][w - 1]
-            for s_, lo, hi in self.halo[dst][w]:
-                if s_ == src:
-                    out.append((so[w - 1] + lo * S, do[w - 1] + lo * S, (hi - lo) * S))
+            for s_, wp, lo, hi in fr:
+                if s_ == src and wp <= k:
+                    S = L.S[k][wp]
+                    out.append((so[wp] + lo * S, do[wp] + lo * S, (hi - lo) * S))
         return out
 
     def recv_elems(self, q: int, k: int | None = None) -> int:
@@ -280,9 +348,10 @@ class SlabChain:
         self.psum = torch.zeros(1, dtype=torch.float64, device=self.probs.device)
         self._xfer = {}
         for k in range(plan.k0, n):
-            sends = [(q, lo, ln) for q in range(plan.world) for lo, _, ln in plan.transfers(k, rank, q)]
-            recvs = [(q, lo, ln) for q in range(plan.world) for _, lo, ln in plan.transfers(k, q, rank)]
-            self._xfer[k] = (sends, recvs)
+            for g in range(plan.groups()):
+                sends = [(q, lo, ln) for q in range(plan.world) for lo, _, ln in plan.transfers(k, rank, q, g)]
+                recvs = [(q, lo, ln) for q in range(plan.world) for _, lo, ln in plan.transfers(k, q, rank, g)]
+                self._xfer[(k, g)] = (sends, recvs)
         self.bytes_received = 16 * plan.recv_elems(rank)
         self.bytes_sent = 16 * plan.send_elems(rank)
         self.bytes = 16 * (ea + eb) + 8 * acc
@@ -295,10 +364,10 @@ class SlabChain:
             self._scratch_buf = self.buf_a.new_empty(elems)
         return self._scratch_buf[:elems]
 
-    def _exchange(self, k: int, buf):
+    def _exchange(self, k: int, g: int, buf):
         import torch
         import torch.distributed as dist
-        sends, recvs = self._xfer[k]
+        sends, recvs = self._xfer[(k, g)]
         if not sends and not recvs:
             return []
         flat = torch.view_as_real(buf)
@@ -332,44 +401,47 @@ class SlabChain:
         else:
             parent = self._buf(0)
             parent[:1] = 1.0               # the vacuum: one prefix of weight 0, one tail
-        works = []
+        groups = []                    # exchange groups that followed layer k-1, in the order the pieces consume them
         mark("replicated")
         for k in range(k0, n + 1):
-            rr = plan.rho_ranges(k, r)
             poff = plan.offsets(k - 1, r)
-            # slabs whose prefix rows are all local run first, while the rows of the others are still on the wire
-            free = [(lo, hi) if not plan.halo[r].get(w) else (0, 0) for w, (lo, hi) in enumerate(rr)]
-            rest = [(lo, hi) if plan.halo[r].get(w) else (0, 0) for w, (lo, hi) in enumerate(rr)]
-            parts = [p_ for p_ in (free, rest) if any(hi > lo for lo, hi in p_)] if works else [rr]
-            for part in parts:
-                if part is rest:
-                    for w_ in works:
+            for g, pc in enumerate(plan.piece[r]):
+                rr = [(0, 0)] * (k + 1)
+                for w, a, b in pc:
+                    if w <= k:
+                        assert rr[w] == (0, 0)
+                        rr[w] = (a, b)
+                if g < len(groups) and groups[g]:
+                    for w_ in groups[g]:           # the rows this piece reads have arrived (earlier groups were waited before)
                         w_.wait()
-                    works = []
-                    mark(f"wait{k}")
+                    groups[g] = []
+                    mark(f"wait{k}.{g}")
+                if not any(hi > lo for lo, hi in rr):
+                    continue
                 if k < n:
-                    self.slab_fn(k, self.order[k - 1], parent, part, poff, plan.offsets(k, r), self._buf(k), None, None)
+                    self.slab_fn(k, self.order[k - 1], parent, rr, poff, plan.offsets(k, r), self._buf(k), None, None)
                 else:
                     if on_last is not None:
                         on_last("begin")
-                    self.slab_fn(k, self.order[k - 1], parent, part, poff, self.out_off, None, self.probs, self.psum)
+                    self.slab_fn(k, self.order[k - 1], parent, rr, poff, self.out_off, None, self.probs, self.psum)
                     if on_last is not None:
                         on_last("end")
             mark(f"layer{k}")
-            for w_ in works:           # sends of layer k-1 read the buffer that layer k+1 is about to overwrite
-                w_.wait()
+            for grp in groups:             # sends of layer k-1 read the buffer that layer k+1 is about to overwrite
+                for w_ in grp:
+                    w_.wait()
             if k < n:
                 buf = self._buf(k)
-                works = self._exchange(k, buf)
+                groups = [self._exchange(k, g, buf) for g in range(plan.groups())]
                 parent = buf
             else:
-                works = []
+                groups = []
         if reduce_sum and plan.world > 1:
             dist.all_reduce(self.psum, op=dist.ReduceOp.SUM, group=self.group)
         return self.probs, self.psum
 
 
-def engine_slab_chain(engine, U_ref, in_state, group=None, shard_min: int = 1 << 23):
+def engine_slab_chain(engine, U_ref, in_state, group=None, shard_min: int = 1 << 23, pieces: int = 4):
     """Device instantiation of SlabChain: kernels from libfock_b200.so (slos_layer, slos_layer_slab), NCCL send / recv."""
     import torch
     import torch.distributed as dist
@@ -380,7 +452,7 @@ def engine_slab_chain(engine, U_ref, in_state, group=None, shard_min: int = 1 <<
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
-    plan = SlabPlan(m, n, world, shard_min=shard_min)
+    plan = SlabPlan(m, n, world, shard_min=shard_min, pieces=pieces)
     L = plan.layout
     order = engine.slos_order(occ)
     inf = prodnfact(occ)

@@ -235,7 +235,7 @@ def test_exchange_chain_gloo(tmp_path, world, pieces, fractions):
     assert all(os.path.exists(os.path.join(str(tmp_path), f"xok{r}")) for r in range(world))
 
 
-def _slab_worker(rank, world, port, outdir, m, in_state, shard_min):
+def _slab_worker(rank, world, port, outdir, m, in_state, shard_min, pieces=4):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -249,9 +249,19 @@ def _slab_worker(rank, world, port, outdir, m, in_state, shard_min):
     ref = oracle.slos_probs(u, in_state)
     order = oracle.slos_order(in_state)
     lib = oracle.lib()
-    plan = slab.SlabPlan(m, n, world, shard_min=shard_min)
+    plan = slab.SlabPlan(m, n, world, shard_min=shard_min, pieces=pieces)
     L = plan.layout
     assert 1 <= plan.k0 <= n
+    # the pieces of a rank tile its own prefixes exactly once
+    for q in range(world):
+        got = sorted(x for pc in plan.piece[q] for x in pc)
+        merged = []
+        for w, a, b in got:
+            if merged and merged[-1][0] == w and merged[-1][2] == a:
+                merged[-1] = (w, merged[-1][1], b)
+            else:
+                merged.append((w, a, b))
+        assert merged == sorted(plan.own[q]), (merged, plan.own[q])
     # ownership tiles the prefix space of every slab exactly once
     for w in range(n + 1):
         spans = sorted((a, b) for q in range(world) for ww, a, b in plan.own[q] if ww == w)
@@ -324,10 +334,11 @@ def _slab_worker(rank, world, port, outdir, m, in_state, shard_min):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,m,in_state,shard_min", [(2, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30), (3, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30),
-                                                        (2, 6, (2, 0, 1, 1, 0, 1), 5), (2, 8, (1, 1, 1, 1, 0, 0, 0, 0), 1 << 40)])
-def test_slab_chain_gloo(tmp_path, world, m, in_state, shard_min):
+@pytest.mark.parametrize("world,m,in_state,shard_min,pieces", [(2, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30, 4), (3, 8, (1, 1, 0, 1, 1, 0, 1, 1), 30, 3),
+                                                               (2, 6, (2, 0, 1, 1, 0, 1), 5, 1), (2, 8, (1, 1, 1, 1, 0, 0, 0, 0), 1 << 40, 2),
+                                                               (3, 12, (1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0), 20, 5)])
+def test_slab_chain_gloo(tmp_path, world, m, in_state, shard_min, pieces):
     """Slab partition at world size 2 / 3 on CPU: fixed prefix ownership, tail parents local, prefix rows
     exchanged as contiguous slab slices; NaN-poisoned buffers prove that every parent a rank reads was owned or received."""
-    mp.spawn(_slab_worker, args=(world, _free_port(), str(tmp_path), m, in_state, shard_min), nprocs=world, join=True)
+    mp.spawn(_slab_worker, args=(world, _free_port(), str(tmp_path), m, in_state, shard_min, pieces), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"sok{r}")) for r in range(world))
