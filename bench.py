@@ -295,6 +295,9 @@ def dist_setup():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL send / recv between two B200s: 634 GB/s one way with the default channel count, 672 GB/s with 64 (tools/p2p_bw.py)
+        for key in ("NCCL_MAX_NCHANNELS", "NCCL_MIN_NCHANNELS", "NCCL_MIN_P2P_NCHANNELS", "NCCL_MAX_P2P_NCHANNELS"):
+            os.environ.setdefault(key, "64")
         try:    # NCCL's copy kernels on a high-priority stream: a halo transfer must not queue behind a 130 000-CTA compute grid
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
@@ -517,7 +520,8 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     elif partition == "slab":
         from perceval_b200 import slab as pslab
         U_ref = [U]
-        chain = pslab.engine_slab_chain(eng, U_ref, in_state, shard_min=args.shard_min, pieces=args.pieces)
+        pieces = args.pieces or (4 if pslab.SlabLayout(m, n).p >= 10 else 1)
+        chain = pslab.engine_slab_chain(eng, U_ref, in_state, shard_min=args.shard_min, pieces=pieces)
         plan = chain.plan
         b, e = 0, chain.probs.numel()          # compact slab-major storage of this rank's prefixes (chain.out_slices)
         get_probs = lambda: chain.probs
@@ -550,12 +554,13 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
         alg_bytes[0] = 16.0 * (rows_last + tails_last) + 8.0 * (e - b)
         desc = (f"slab partition: layers < {plan.k0} replicated; layers {plan.k0}..{n} stored slab-major (prefix weight over the first "
                 f"{Lh.p} modes, prefix rank, tail rank), every rank owns a fixed run of prefixes, tail parents local, prefix rows "
-                f"received over NVLink (NCCL send/recv of contiguous slab slices); output stays sharded in slab-major order")
+                f"received over NVLink (NCCL send/recv of contiguous slab slices, {pieces} piece(s) / exchange group(s) per layer); output "
+                f"stays sharded in slab-major order")
         nvlink = {"bytes_received_per_step": int(chain.bytes_received), "bytes_sent_per_step": int(chain.bytes_sent)}
     else:
         U_ref = [U]
         shard_min = (1 << 62) if partition == "replicate" else args.shard_min
-        chain = pdist.engine_exchange_chain(eng, U_ref, in_state, pieces=args.pieces, shard_min=shard_min)
+        chain = pdist.engine_exchange_chain(eng, U_ref, in_state, pieces=args.pieces or 4, shard_min=shard_min)
         b, e = chain.begin, chain.end
         get_probs = lambda: chain.probs
         get_sum = lambda: chain.psum
@@ -575,7 +580,7 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
         need_last = sum(hi - lo for segs in plan.need[n][rank] for lo, hi in segs) if plan.k0 < n else eng.count(m, n - 1)
         alg_bytes[0] = 16.0 * min(need_last, eng.count(m, n - 1)) + 8.0 * (e - b)
         desc = (f"owner-computes + halo exchange: layers < {plan.k0} replicated, layers {plan.k0}..{n} cut in {world} rank ranges "
-                f"x {args.pieces} pieces, parents sent over NVLink (NCCL send/recv) in groups ordered by the consumer's pieces"
+                f"x {args.pieces or 4} pieces, parents sent over NVLink (NCCL send/recv) in groups ordered by the consumer's pieces"
                 if plan.k0 < n else f"output layer cut in {world} rank ranges, layers 1..{n - 1} replicated on every rank, no exchange")
         nvlink = {"bytes_received_per_step": int(chain.bytes_received), "bytes_sent_per_step": int(chain.bytes_sent)}
 
@@ -903,7 +908,7 @@ def main():
                     help="N > 1: slab = prefix slabs owned by rank, prefix rows over NVLink (default when two whole layers fit); "
                          "replicate = lower layers on every rank, output layer sharded by rank range; exchange = rank ranges + NVLink "
                          "halo exchange; windowed = recompute-window chain (no exchange, the only one that fits 14/28)")
-    ap.add_argument("--pieces", type=int, default=4, help="slab / exchange: pieces per rank and layer = exchange groups per layer")
+    ap.add_argument("--pieces", type=int, default=0, help="slab / exchange: pieces per rank and layer = exchange groups per layer (0: slab takes 4 with >= 10 prefix modes, where the windows of consecutive pieces are nearly disjoint -- 14/28 --, else 1; exchange takes 4)")
     ap.add_argument("--shard-min", type=int, default=1 << 23, help="exchange: layers with fewer states are replicated")
     ap.add_argument("--sub", type=int, default=0, help="windowed: sub-shards per rank (0 = from free memory)")
     ap.add_argument("--spot", type=int, default=64, help="outputs (per rank) checked against the CPU oracle outside the timed region")
