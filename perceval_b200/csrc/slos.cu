@@ -18,6 +18,7 @@
 #include "slos_tile.cuh"
 
 #define SLOS_BLOCK 256
+#define SLOS_SUB0_MIN (1ull << 18)   // smallest weight-0 tile that goes to a sub-layer call (slos_layer_impl)
 
 struct SlosArgs {
     int m, k, mk;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
         s_bt[i] = a.bt[i];
         s_dt[i] = a.dt[i];
     }
-    for (int i = tid; i < m; i += TILE_BLOCK) s_u[i] = a.U[(size_t)i * m + a.mk];
+    for (int i = tid; i < m; i += TILE_BLOCK) s_u[i] = a.U[(size_t)(a.urow0 + i) * a.ustride + a.mk];
     if (tid == 0) {
         double f = 1.0;
         s_fact[0] = 1.0;
@@ -540,7 +541,8 @@ struct SlabSpec {
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
                             uint64_t ce, cudaStream_t st, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
-                            uint64_t gap_e = UINT64_MAX, const SlabSpec *slab = nullptr) {
+                            uint64_t gap_e = UINT64_MAX, const SlabSpec *slab = nullptr, bool skip_w0 = false, int ustride = 0,
+                            int urow0 = 0) {
     // gfilter: 0 = every class (tile kernel), 1 = only classes whose tail block fills a CTA (S >= 256) in the hybrid thin
     //          kernel (slos_thin.cu), 2 = only the small classes (S < 256) in the tile kernel
     const int p = m - D;
@@ -563,12 +565,14 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     a.cbegin = cb; a.cend = ce;
     a.status = c->d_status;
     a.slab = slab ? 1 : 0;
+    a.ustride = ustride > 0 ? ustride : m;
+    a.urow0 = urow0;
     const bool full = slab != nullptr || (cb == 0 && ce == fock_count(m, k));
     uint64_t items = 0;
     int ncls = 0;
     // classes with small tail blocks first: their CTAs walk many prefixes with little work each and would otherwise run
     // alone at the end of the grid
-    for (int w = k; w >= 0; --w) {
+    for (int w = k; w >= (skip_w0 ? 1 : 0); --w) {
         const int u = k - w;
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
@@ -664,12 +668,28 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
         const bool gapped = gap_b < gap_e && gap_b < pe;
         const bool parent_full = (pb == 0 && pe == fock_count(m, k - 1)) && !gapped;
         const int D = slos_tail_modes(m);
+        // The slab of prefix weight 0 (every photon in the tail: ONE prefix, 2 % of the states at 12/24) is an independent
+        // layer on the D tail modes.  A sweep over one prefix does not amortise the per-thread tail set-up (73 ps per state
+        // against 12.7 ps elsewhere), so a whole layer hands that block to a sub-layer call with its own prefix/tail split
+        // (same modes in the same order: results are bit-identical).
+        const bool full = cb == 0 && ce == fock_count(m, k);
+        const int Dsub = D > 0 ? slos_tail_modes(D) : 0;
+        const bool sub0 = force == 0 && full && parent_full && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN && ((uintptr_t)d_parent & 15) == 0;
+        if (sub0) {
+            const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1), cbase = fock_count(m, k) - S, pbase = fock_count(m, k - 1) - Sp;
+            if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * pbase, 0, Sp, d_child ? d_child + 2 * cbase : nullptr,
+                                          d_probs ? d_probs + cbase : nullptr, d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX,
+                                          nullptr, false, m, m - D)) return rc;
+        }
         const bool thin = force == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
         if (D > 0 && thin && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
-            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1)) return rc;
-            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 2);
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1,
+                                          UINT64_MAX, UINT64_MAX, nullptr, sub0)) return rc;
+            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 2,
+                                    UINT64_MAX, UINT64_MAX, nullptr, sub0);
         }
-        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gap_b, gap_e);
+        if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gap_b, gap_e,
+                                           nullptr, sub0);
     }
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
@@ -771,15 +791,25 @@ extern "C" int slos_layer_slab(fock_ctx *c, int m, int k, int p, const double *d
     for (int w = 0; w <= k; ++w) children += (h_rho_ranges[2 * w + 1] - h_rho_ranges[2 * w]) * fock_count(D, k - w);
     if (children == 0) return FOCK_OK;
     const uint64_t np = fock_count(m, k - 1), nc = fock_count(m, k);
+    // the weight-0 slab as a sub-layer on the tail modes (see slos_layer_impl)
+    const int Dsub = slos_tail_modes(D);
+    const bool sub0 = h_rho_ranges[1] > h_rho_ranges[0] && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN;
+    if (sub0) {
+        const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1);
+        if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * h_parent_slab_off[0], 0, Sp,
+                                      d_child ? d_child + 2 * h_child_slab_off[0] : nullptr, d_probs ? d_probs + h_child_slab_off[0] : nullptr,
+                                      d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX, nullptr, false, m, m - D)) return rc;
+        if (children == fock_count(D, k)) return FOCK_OK;
+    }
     const bool thin = d_probs != nullptr && D == 16 && m - D <= 8 && children >= (1ull << 24) && slos_thin_supports(D, k);
     if (thin) {
         if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 1,
-                                      UINT64_MAX, UINT64_MAX, &spec)) return rc;
+                                      UINT64_MAX, UINT64_MAX, &spec, sub0)) return rc;
         return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 2, UINT64_MAX,
-                                UINT64_MAX, &spec);
+                                UINT64_MAX, &spec, sub0);
     }
     return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 0, UINT64_MAX,
-                            UINT64_MAX, &spec);
+                            UINT64_MAX, &spec, sub0);
 }
 
 extern "C" int slos_probs_epilogue(fock_ctx *c, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,

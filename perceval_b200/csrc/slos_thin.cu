@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TH_MINB) slos_thin6_kernel(const _
     __shared__ double s_red[TILE_BLOCK / 32];
     const uint64_t *__restrict__ dt = a.dt;
 
-    for (int i = tid; i < m; i += TILE_BLOCK) sh.s_u[i] = a.U[(size_t)i * m + a.mk];
+    for (int i = tid; i < m; i += TILE_BLOCK) sh.s_u[i] = a.U[(size_t)(a.urow0 + i) * a.ustride + a.mk];
     int ci = 0;
     for (int c = 1; c < a.ncls; ++c)
         if ((uint64_t)blockIdx.x >= a.cls[c].item_begin) ci = c;
@@ -368,7 +368,7 @@ int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want
     if (!ds.done[slot]) FOCK_CUDA(cudaEventCreateWithFlags(&ds.done[slot], cudaEventDisableTiming));
     else FOCK_CUDA(cudaStreamWaitEvent(st, ds.done[slot], 0));
     a.uslot = (int)slot;
-    FOCK_CUDA(cudaMemcpy2DAsync((char *)sym + (size_t)slot * FOCK_QMAX * 16, 16, a.U + a.mk, (size_t)a.m * 16, 16, (size_t)a.m,
+    FOCK_CUDA(cudaMemcpy2DAsync((char *)sym + (size_t)slot * FOCK_QMAX * 16, 16, a.U + (size_t)a.urow0 * a.ustride + a.mk, (size_t)a.ustride * 16, 16, (size_t)a.m,
                                 cudaMemcpyDeviceToDevice, st));
     if (int rc = th_launch(a, want_child, want_probs, rangechk, grid, smem, st)) return rc;
     FOCK_CUDA(cudaEventRecord(ds.done[slot], st));

@@ -515,7 +515,7 @@ def test_two_streams_thin_kernel(eng, oracle):
 
 # ---------------------------------------------------------------- slab-major layout (multi-GPU slab partition)
 
-@pytest.mark.parametrize("m,k", [(8, 4), (12, 6), (16, 8), (20, 7), (24, 6)])
+@pytest.mark.parametrize("m,k", [(8, 4), (12, 6), (16, 8), (20, 7), (24, 6), (20, 9)])
 def test_slos_layer_slab_equals_rank_order_layer(eng, oracle, m, k):
     """slos_layer_slab (slab-major parent and child) == slos_layer (FSArray rank order) under the block permutation, bit for
     bit (same kernels, same accumulation order), for whole layers, for partial prefix ranges with compact child offsets, and
@@ -582,4 +582,21 @@ def test_slab_chain_single_rank_matches_distribution(eng, oracle, m, st, shard_m
         want[perm] = ref
         assert torch.equal(probs[off:off + ln], want[base:base + ln])
     assert abs(psum.item() - 1.0) < 1e-12
+    eng.check_status()
+
+
+@pytest.mark.parametrize("m,st", [(20, (1,) * 9 + (0,) * 11), (22, (2, 1, 1, 1, 1, 1, 1) + (0,) * 15), (24, (1,) * 8 + (0,) * 16)])
+def test_weight0_slab_sub_layer_vs_oracle(eng, oracle, m, st):
+    """Whole layers hand the slab of prefix weight 0 (all photons in the 16 tail modes) to a sub-layer call on those modes once
+    it holds >= 2^18 states: the full chain (coefficients, probabilities, sum) against the oracle at sizes where that path is
+    taken for the last layers, and bit-identical to the kernels pinned to the plain tile path."""
+    u = oracle.random_unitary(m, seed=19)
+    U = eng.unitary(u)
+    assert oracle.count(16, sum(st)) >= 1 << 18
+    probs, psum, coefs = eng.slos_probs(U, st, want_coefs=True)
+    assert rel_err(coefs.cpu().numpy(), oracle.slos_coefs(u, st)) < REL
+    assert rel_err(probs.cpu().numpy(), oracle.slos_probs(u, st)) < REL
+    assert abs(float(psum.item()) - 1.0) < 1e-12
+    p2, s2, _ = eng.slos_probs(U, st, want_coefs=False)
+    assert torch.equal(p2, probs)
     eng.check_status()
