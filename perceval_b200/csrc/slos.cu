@@ -333,10 +333,6 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
             uint64_t base = 0, E = 0;
             int nz = 0;
             double pf = 1.0;
-            if (a.has_ext) {   // the row of the (earlier) mode this sub-layer's prefix e_j holds its photon in: accumulated first
-                e_u[tid * maxnz] = a.U[(size_t)a.ext_urow * a.ustride + a.mk];
-                nz = 1;
-            }
             for (int i = 0; i < p; ++i) {
                 int T = 0;
                 if (i < p - 1) {
@@ -368,8 +364,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
                 for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = a.cls[ci].roff + (rho - e_pb[tid * maxnz + e]) * S;
                 tb = a.cls[ci].toff + rho * a.cls[ci].Sp;
             } else {
-                for (int e = a.has_ext; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
-                if (a.has_ext) e_pb[tid * maxnz] = a.ext_off + base;
+                for (int e = 0; e < nz; ++e) e_pb[tid * maxnz + e] = base - e_pb[tid * maxnz + e];
                 tb = base - E;   // only meaningful (and only used) when u >= 1
             }
             TileDesc td;
@@ -546,19 +541,16 @@ struct SlabSpec {
 static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U, int mk, const double *d_parent, uint64_t pb,
                             uint64_t pe, double *d_child, double *d_probs, double *d_sum, double in_prodnfact, uint64_t cb,
                             uint64_t ce, cudaStream_t st, int gfilter = 0, uint64_t gap_b = UINT64_MAX,
-                            uint64_t gap_e = UINT64_MAX, const SlabSpec *slab = nullptr, int skip_below = 0, int ustride = 0,
-                            int urow0 = 0, int ext_urow = -1, uint64_t ext_off = 0) {
+                            uint64_t gap_e = UINT64_MAX, const SlabSpec *slab = nullptr, bool skip_w0 = false, int ustride = 0,
+                            int urow0 = 0) {
     // gfilter: 0 = every class (tile kernel), 1 = only classes whose tail block fills a CTA (S >= 256) in the hybrid thin
     //          kernel (slos_thin.cu), 2 = only the small classes (S < 256) in the tile kernel
     const int p = m - D;
     TileArgs a;
     memset(&a, 0, sizeof a);
     a.m = m; a.k = k; a.mk = mk; a.p = p;
-    a.maxnz = (p < k ? p : k) + (ext_urow >= 0 ? 1 : 0);
+    a.maxnz = p < k ? p : k;
     if (a.maxnz < 1) a.maxnz = 1;
-    a.has_ext = ext_urow >= 0 ? 1 : 0;
-    a.ext_urow = ext_urow >= 0 ? ext_urow : 0;
-    a.ext_off = ext_off;
     a.bt = c->d_bt; a.dt = c->d_dt;
     a.U = (const double2 *)d_U;
     a.parent = (const double2 *)d_parent;
@@ -580,7 +572,7 @@ static int slos_layer_tiles(fock_ctx *c, int D, int m, int k, const double *d_U,
     int ncls = 0;
     // classes with small tail blocks first: their CTAs walk many prefixes with little work each and would otherwise run
     // alone at the end of the grid
-    for (int w = k; w >= skip_below; --w) {
+    for (int w = k; w >= (skip_w0 ? 1 : 0); --w) {
         const int u = k - w;
         const uint64_t np_total = fock_count(p, w), S64 = fock_count(D, u);
         FOCK_REQUIRE(S64 < (1ull << 32), FOCK_ERR_LIMIT, "slos: tail block too large for the tile kernel");
@@ -683,36 +675,21 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
         const bool full = cb == 0 && ce == fock_count(m, k);
         const int Dsub = D > 0 ? slos_tail_modes(D) : 0;
         const bool sub0 = force == 0 && full && parent_full && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN && ((uintptr_t)d_parent & 15) == 0;
-        int skip = 0;
         if (sub0) {
-            const int p = m - D;
             const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1), cbase = fock_count(m, k) - S, pbase = fock_count(m, k - 1) - Sp;
             if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * pbase, 0, Sp, d_child ? d_child + 2 * cbase : nullptr,
                                           d_probs ? d_probs + cbase : nullptr, d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX,
-                                          nullptr, 0, m, p)) return rc;
-            skip = 1;
-            // the p prefixes of weight 1 (e_j): the same sub-layer with k-1 photons plus ONE aligned row, U[j,mk] * the weight-0
-            // block of the parent layer (8 prefixes per sweep: 20 ps per state against 12.7)
-            if (k >= 2 && p >= 1 && Sp >= SLOS_SUB0_MIN) {
-                const uint64_t Spp = fock_count(D, k - 2);
-                for (int j = 0; j < p; ++j) {
-                    const uint64_t cb1 = host_prefix_base(m, p, 1, k - 1, (uint64_t)j), pb1 = host_prefix_base(m, p, 1, k - 2, (uint64_t)j);
-                    if (int rc = slos_layer_tiles(c, Dsub, D, k - 1, d_U, mk, d_parent + 2 * pb1, 0, Spp, d_child ? d_child + 2 * cb1 : nullptr,
-                                                  d_probs ? d_probs + cb1 : nullptr, d_sum, in_prodnfact, 0, Sp, st, 0, UINT64_MAX, UINT64_MAX,
-                                                  nullptr, 0, m, p, j, pbase - pb1)) return rc;
-                }
-                skip = 2;
-            }
+                                          nullptr, false, m, m - D)) return rc;
         }
         const bool thin = force == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
         if (D > 0 && thin && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
             if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1,
-                                          UINT64_MAX, UINT64_MAX, nullptr, skip)) return rc;
+                                          UINT64_MAX, UINT64_MAX, nullptr, sub0)) return rc;
             return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 2,
-                                    UINT64_MAX, UINT64_MAX, nullptr, skip);
+                                    UINT64_MAX, UINT64_MAX, nullptr, sub0);
         }
         if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gap_b, gap_e,
-                                           nullptr, skip);
+                                           nullptr, sub0);
     }
     SlosArgs a;
     a.m = m; a.k = k; a.mk = mk;
@@ -814,41 +791,25 @@ extern "C" int slos_layer_slab(fock_ctx *c, int m, int k, int p, const double *d
     for (int w = 0; w <= k; ++w) children += (h_rho_ranges[2 * w + 1] - h_rho_ranges[2 * w]) * fock_count(D, k - w);
     if (children == 0) return FOCK_OK;
     const uint64_t np = fock_count(m, k - 1), nc = fock_count(m, k);
-    // the slabs of prefix weight 0 and 1 as sub-layers on the tail modes (see slos_layer_impl)
+    // the weight-0 slab as a sub-layer on the tail modes (see slos_layer_impl)
     const int Dsub = slos_tail_modes(D);
-    int skip = 0;
-    uint64_t done = 0;
-    if (Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN) {
+    const bool sub0 = h_rho_ranges[1] > h_rho_ranges[0] && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN;
+    if (sub0) {
         const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1);
-        if (h_rho_ranges[1] > h_rho_ranges[0]) {
-            if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * h_parent_slab_off[0], 0, Sp,
-                                          d_child ? d_child + 2 * h_child_slab_off[0] : nullptr, d_probs ? d_probs + h_child_slab_off[0] : nullptr,
-                                          d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX, nullptr, 0, m, p)) return rc;
-            done += S;
-        }
-        skip = 1;
-        if (k >= 2 && p >= 1 && Sp >= SLOS_SUB0_MIN) {
-            const uint64_t Spp = fock_count(D, k - 2);
-            for (uint64_t j = h_rho_ranges[2]; j < h_rho_ranges[3]; ++j) {
-                const uint64_t cb1 = h_child_slab_off[1] + j * Sp, pb1 = h_parent_slab_off[1] + j * Spp;
-                if (int rc = slos_layer_tiles(c, Dsub, D, k - 1, d_U, mk, d_parent + 2 * pb1, 0, Spp, d_child ? d_child + 2 * cb1 : nullptr,
-                                              d_probs ? d_probs + cb1 : nullptr, d_sum, in_prodnfact, 0, Sp, st, 0, UINT64_MAX, UINT64_MAX,
-                                              nullptr, 0, m, p, (int)j, h_parent_slab_off[0] - pb1)) return rc;
-                done += Sp;
-            }
-            skip = 2;
-        }
-        if (done == children) return FOCK_OK;
+        if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * h_parent_slab_off[0], 0, Sp,
+                                      d_child ? d_child + 2 * h_child_slab_off[0] : nullptr, d_probs ? d_probs + h_child_slab_off[0] : nullptr,
+                                      d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX, nullptr, false, m, m - D)) return rc;
+        if (children == fock_count(D, k)) return FOCK_OK;
     }
     const bool thin = d_probs != nullptr && D == 16 && m - D <= 8 && children >= (1ull << 24) && slos_thin_supports(D, k);
     if (thin) {
         if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 1,
-                                      UINT64_MAX, UINT64_MAX, &spec, skip)) return rc;
+                                      UINT64_MAX, UINT64_MAX, &spec, sub0)) return rc;
         return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 2, UINT64_MAX,
-                                UINT64_MAX, &spec, skip);
+                                UINT64_MAX, &spec, sub0);
     }
     return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 0, UINT64_MAX,
-                            UINT64_MAX, &spec, skip);
+                            UINT64_MAX, &spec, sub0);
 }
 
 extern "C" int slos_probs_epilogue(fock_ctx *c, int m, int n, const double *d_coefs, double in_prodnfact, double *d_probs,

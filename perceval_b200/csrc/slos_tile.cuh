@@ -31,8 +31,6 @@ struct TileArgs {
     uint64_t cbegin, cend;
     int *status;
     int ustride, urow0;        // column mk of the unitary = U[(urow0 + i) * ustride + mk], i < m (a sub-layer on the tail modes reads rows p..)
-    int has_ext, ext_urow;     // sub-layer of a weight-1 prefix e_j: one extra aligned row, U[ext_urow, mk] * parent[ext_off + rank], added first
-    uint64_t ext_off;
     int slab;                  // 0: parent and child in FSArray rank order; 1: slab-major (offsets in TileClass), see slos_layer_slab
     int uslot;                 // thin kernel: which constant-bank copy of the unitary column this launch reads
     TileClass cls[FOCK_TMAX];
