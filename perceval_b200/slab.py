@@ -133,6 +133,8 @@ class SlabPlan:
         # with few prefixes (w = 0: one prefix, 2 % of the states of 12/24) amortise that over little work.  c = 12.2 ps,
         # s = 61 ps fitted to the measured single-GPU layer (14.6 ps per state) and to a rank that held only w <= 2 (21 ps).
         def per_state(w):
+            if w == 0 and L.S[n][0] >= (1 << 18) and tail_modes(L.D) > 0:
+                return 22.0     # a whole weight-0 slab runs as a sub-layer on the tail modes (csrc/slos.cu), not as a one-prefix sweep
             return 12.2 + 61.0 / min(max(L.nprefix[w], 1), 128)
         cost = [int(1000 * per_state(w)) * sum(L.S[k][w] for k in range(max(self.k0, w), n + 1)) for w in range(n + 1)]
         total = sum(L.nprefix[w] * cost[w] for w in range(n + 1))
