@@ -413,9 +413,9 @@ class SlabChain:
                     if w <= k:
                         assert rr[w] == (0, 0)
                         rr[w] = (a, b)
-                if g < len(groups) and groups[g]:
-                    for w_ in groups[g]:           # the rows this piece reads have arrived (earlier groups were waited before)
-                        w_.wait()
+                if g < len(groups) and groups[g] and self._xfer[(k - 1, g)][1]:
+                    for w_ in groups[g]:           # the rows this piece reads have arrived (earlier groups were waited before);
+                        w_.wait()                  # a group in which this rank only SENDS is waited for at the end of the layer
                     groups[g] = []
                     mark(f"wait{k}.{g}")
                 if not any(hi > lo for lo, hi in rr):
