@@ -138,35 +138,66 @@ class SlabPlan:
             return 12.2 + 61.0 / min(max(L.nprefix[w], 1), 128)
         cost = [int(1000 * per_state(w)) * sum(L.S[k][w] for k in range(max(self.k0, w), n + 1)) for w in range(n + 1)]
         total = sum(L.nprefix[w] * cost[w] for w in range(n + 1))
-        self.own = [[] for _ in range(world)]
-        cum, q = 0, 0
-        for w in range(n + 1):
-            sw, a = cost[w], 0
-            while a < L.nprefix[w]:
-                room = total * (q + 1) // world - cum
-                take = min(L.nprefix[w] - a, max(1, -(-room // sw))) if (room > 0 or q == world - 1) else 0
-                if take == 0:
-                    q += 1
-                    continue
-                self.own[q].append((w, a, a + take))
-                cum += take * sw
-                a += take
-                if cum >= total * (q + 1) // world and q < world - 1:
-                    q += 1
-        # merge adjacent runs of the same slab
-        for q in range(world):
-            merged = []
-            for w, a, b in self.own[q]:
-                if merged and merged[-1][0] == w and merged[-1][2] == a:
-                    merged[-1] = (w, merged[-1][1], b)
-                else:
-                    merged.append((w, a, b))
-            self.own[q] = merged
+
+        def cut(targets):
+            """contiguous runs of whole prefixes whose cumulated cost follows ``targets`` (cumulative, per rank)"""
+            own = [[] for _ in range(world)]
+            cum, q = 0, 0
+            for w in range(n + 1):
+                sw, a = cost[w], 0
+                while a < L.nprefix[w]:
+                    room = targets[q] - cum
+                    take = min(L.nprefix[w] - a, max(1, -(-room // sw))) if (room > 0 or q == world - 1) else 0
+                    if take == 0:
+                        q += 1
+                        continue
+                    if own[q] and own[q][-1][0] == w and own[q][-1][2] == a:
+                        own[q][-1] = (w, own[q][-1][1], a + take)
+                    else:
+                        own[q].append((w, a, a + take))
+                    cum += take * sw
+                    a += take
+                    if cum >= targets[q] and q < world - 1:
+                        q += 1
+            return own
+
+        def owners_of(own):
+            owners = {}
+            for q in range(world):
+                for w, a, b in own[q]:
+                    owners.setdefault(w, []).append((q, a, b))
+            return owners
+
+        def remote_rows(own, owners, q):
+            """[(src, w-1, lo, hi)] prefix rows rank q reads and does not own"""
+            rows = []
+            for w, a, b in own[q]:
+                if w >= 1:
+                    for lo, hi in P.parent_segments(L.p, w, [(a, b)], max_segments=4):
+                        for src, sa, sb in owners.get(w - 1, []):
+                            if src != q:
+                                x, y = max(lo, sa), min(hi, sb)
+                                if y > x:
+                                    rows.append((src, w - 1, x, y))
+            return rows
+
+        # a rank that waits for rows does less in the same time: the cost a rank is given = its share of (compute + everybody's
+        # transfers) minus its own transfer time (NCCL send / recv between B200s: ~0.55 B / ps while a rank sends and receives)
+        self.own = cut([total * (q + 1) // world for q in range(world)])
+        for _ in range(3 if world > 1 else 0):
+            owners = owners_of(self.own)
+            comm = []
+            for q in range(world):
+                elems = sum((hi - lo) * sum(L.S[k][wp] for k in range(max(self.k0, wp), n)) for src, wp, lo, hi in remote_rows(self.own, owners, q))
+                comm.append(int(1000 * 16 * elems / 0.55))
+            share = (total + sum(comm)) // world
+            acc, targets = 0, []
+            for q in range(world):
+                acc += max(share - comm[q], total // (8 * world))
+                targets.append(acc)
+            self.own = cut([t * total // max(targets[-1], 1) for t in targets])
         self._storage = {}
-        self._owners = {}
-        for q in range(world):
-            for w, a, b in self.own[q]:
-                self._owners.setdefault(w, []).append((q, a, b))
+        self._owners = owners_of(self.own)
         # rows[q][w] = merged rho' segments of slab w-1 that q's part of slab w reads through prefix modes (owned or not)
         self.rows = [{} for _ in range(world)]
         for q in range(world):
@@ -182,24 +213,33 @@ class SlabPlan:
         self.piece = [[] for _ in range(world)]         # piece[q][g] = [(w, a, b)]
         self.fresh = [[] for _ in range(world)]         # fresh[q][g] = [(src, w-1, lo, hi)] rows to receive before piece g
         for q in range(world):
+            # runs whose rows are all local form their own pieces (they never wait), the others are cut by modelled cost
+            free_runs = [(w, a, b) for w, a, b in self.own[q] if not remote_rows([[(w, a, b)] if r == q else [] for r in range(world)], self._owners, q)]
+            rest_runs = [x for x in self.own[q] if x not in free_runs]
             mine = sum((b - a) * cost[w] for w, a, b in self.own[q])
-            target = max(1, -(-mine // max(1, pieces)))
-            cur, acc, out = [], 0, []
-            for w, a, b in self.own[q]:
-                while a < b:
-                    room = target - acc
-                    take = min(b - a, max(1, room // max(cost[w], 1)))
-                    if cur and cur[-1][0] == w and cur[-1][2] == a:
-                        cur[-1] = (w, cur[-1][1], a + take)
-                    else:
-                        cur.append((w, a, a + take))
-                    acc += take * cost[w]
-                    a += take
-                    if acc >= target:
-                        out.append(cur)
-                        cur, acc = [], 0
-            if cur:
-                out.append(cur)
+            out = []
+            for runs in (free_runs, rest_runs):
+                part = sum((b - a) * cost[w] for w, a, b in runs)
+                if part == 0:
+                    continue
+                npc = max(1, round(pieces * part / max(mine, 1)))
+                target = max(1, -(-part // npc))
+                cur, acc = [], 0
+                for w, a, b in runs:
+                    while a < b:
+                        room = target - acc
+                        take = min(b - a, max(1, room // max(cost[w], 1)))
+                        if cur and cur[-1][0] == w and cur[-1][2] == a:
+                            cur[-1] = (w, cur[-1][1], a + take)
+                        else:
+                            cur.append((w, a, a + take))
+                        acc += take * cost[w]
+                        a += take
+                        if acc >= target:
+                            out.append(cur)
+                            cur, acc = [], 0
+                if cur:
+                    out.append(cur)
             need = []
             for pc in out:
                 rows = []
