@@ -496,7 +496,7 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
     if partition == "auto":
         from perceval_b200 import slab as pslab
         free, _tot = torch.cuda.mem_get_info(dev)
-        sp = pslab.SlabPlan(m, n, world, shard_min=args.shard_min)
+        sp = pslab.SlabPlan(m, n, world, shard_min=args.shard_min, pieces=args.pieces or (4 if pslab.SlabLayout(m, n).p >= 10 else 1))
         need = max(16 * sum(sp.buffer_elems(q)) + 8 * sp.own_elems(n, q) for q in range(world))
         partition = "slab" if need < 0.85 * free else "windowed"
     events = []          # (begin, end) CUDA events around every last-layer launch of a step

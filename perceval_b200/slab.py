@@ -189,7 +189,7 @@ class SlabPlan:
             comm = []
             for q in range(world):
                 elems = sum((hi - lo) * sum(L.S[k][wp] for k in range(max(self.k0, wp), n)) for src, wp, lo, hi in remote_rows(self.own, owners, q))
-                comm.append(int(1000 * 16 * elems / 0.55))
+                comm.append(int(1000 * 16 * elems / 0.55) // max(1, pieces))   # with several pieces only the first group is exposed
             share = (total + sum(comm)) // world
             acc, targets = 0, []
             for q in range(world):
