@@ -189,7 +189,9 @@ class SlabPlan:
             comm = []
             for q in range(world):
                 elems = sum((hi - lo) * sum(L.S[k][wp] for k in range(max(self.k0, wp), n)) for src, wp, lo, hi in remote_rows(self.own, owners, q))
-                comm.append(int(1000 * 16 * elems / 0.55) // max(1, pieces))   # with several pieces only the first group is exposed
+                # with several pieces per layer the transfer hides behind the computation (14/28: 187 ms with the plain cost
+                # balance, 201 ms with a quarter of the transfer charged, 221 ms with all of it): charge it only when un-pipelined
+                comm.append(int(1000 * 16 * elems / 0.55) if pieces <= 1 else 0)
             share = (total + sum(comm)) // world
             acc, targets = 0, []
             for q in range(world):
