@@ -283,9 +283,7 @@ class ExchangePlan:
                 k0 = k
                 break
         self.k0 = max(1, min(k0, n))
-        if fractions is None:
-            fractions = balanced_fractions(m, n, world)
-        self.fractions = fractions
+        self.fractions = fractions      # optional rank-space cut points [0, f1, .., 1]; None: equal counts
         self.own = {}      # k -> [(b, e)] per rank
         self.piece = {}    # k -> per rank, [(b, e)] per piece
         for k in range(self.k0, n + 1):
@@ -342,37 +340,6 @@ class ExchangePlan:
                     tot += sum(hi - lo for lo, hi in self.transfers(kk, g, r, q))
         return tot
 
-    def model_ms(self, ps_per_state=None, nvlink_gbs: float = 600.0) -> float:
-        """modelled step time (ms): per layer, every rank computes its pieces as their groups arrive; a group takes the time of
-        its busiest rank (max of bytes sent and received) at ``nvlink_gbs``.  ps_per_state: {k: picoseconds per child}."""
-        n, W = self.n, self.world
-        ps = ps_per_state or {}
-        t_all = 0.0
-        arrive = None
-        for k in range(self.k0, n + 1):
-            cost = ps.get(k, 14.6 if k == n else 15.9) * 1e-9      # ms per child state
-            finish = []
-            for r in range(W):
-                t = 0.0
-                for j, (b, e) in enumerate(self.piece[k][r]):
-                    if arrive is not None and j < len(arrive):
-                        t = max(t, arrive[j])
-                    t += (e - b) * cost
-                finish.append(t)
-            t_layer = max(finish)
-            t_all += t_layer
-            if k < n:
-                arrive, t = [], 0.0
-                for g in range(self.groups(k)):
-                    worst = 0
-                    for r in range(W):
-                        rx = sum(hi - lo for q in range(W) for lo, hi in self.transfers(k, g, q, r))
-                        tx = sum(hi - lo for q in range(W) for lo, hi in self.transfers(k, g, r, q))
-                        worst = max(worst, rx, tx)
-                    t += 16.0 * worst / (nvlink_gbs * 1e6)
-                    arrive.append(t)
-        return t_all
-
 
 def _subtract(segs, seen):
     """parts of ``segs`` not covered by the sorted, merged ranges ``seen``"""
@@ -392,16 +359,6 @@ def _subtract(segs, seen):
         if cur < hi:
             out.append((cur, hi))
     return out
-
-
-# Rank-space fractions of the own ranges, tuned offline with ExchangePlan.model_ms (tools_balance_exchange.py): ranks early
-# in FSArray order read parents spread over most of the previous layer and late ranks are read by everybody, so equal
-# counts leave the NVLink traffic 20x apart between ranks.  {(m, n, world): [0, f1, ..., 1]}; anything else: equal counts.
-BALANCED_FRACTIONS: dict = {}
-
-
-def balanced_fractions(m: int, n: int, world: int):
-    return BALANCED_FRACTIONS.get((m, n, world))
 
 
 class ExchangeChain:
