@@ -497,7 +497,7 @@ def run_slos_multi(args, torch, dist, world, rank, local_rank, barrier, rmax):
         from perceval_b200 import slab as pslab
         free, _tot = torch.cuda.mem_get_info(dev)
         sp = pslab.SlabPlan(m, n, world, shard_min=args.shard_min, pieces=args.pieces or (4 if pslab.SlabLayout(m, n).p >= 10 else 1))
-        need = max(16 * sum(sp.buffer_elems(q)) + 8 * sp.own_elems(n, q) for q in range(world))
+        need = max(16 * sum(sp.buffer_elems(q)) + 8 * sp.own_elems(n, q) for q in range(world)) + pdist.tail_table_bytes(n)
         partition = "slab" if need < 0.85 * free else "windowed"
     events = []          # (begin, end) CUDA events around every last-layer launch of a step
     alg_bytes = [0.0]

@@ -158,10 +158,17 @@ def windowed_buffer_elems(n: int, pieces):
     return a, b
 
 
+def tail_table_bytes(n: int, D: int = 16) -> int:
+    """Device bytes of the cached tail occupation tables (csrc/slos_mu.cu): 8 B per tail rank of FS(D, u), u <= n."""
+    from . import partition as P
+    return 8 * P.count(D + 1, n)
+
+
 def windowed_peak_bytes(n: int, pieces) -> int:
-    """Device bytes of a WindowedChain: both layer buffers plus the probabilities of the rank's whole range."""
+    """Device bytes of a WindowedChain: both layer buffers, the probabilities of the rank's whole range and the library's
+    cached tail tables (1.2 GB at 14 photons)."""
     a, b = windowed_buffer_elems(n, pieces)
-    return 16 * (a + b) + 8 * sum(e - bb for bb, e, _ in pieces)
+    return 16 * (a + b) + 8 * sum(e - bb for bb, e, _ in pieces) + tail_table_bytes(n)
 
 
 def windowed_candidates(sub: int | None = None):
