@@ -96,6 +96,12 @@ extern "C" int fock_create(int device, fock_ctx **out) {
     c->launches = 0;
     c->mu_state = nullptr;
     c->ev_begin = c->ev_end = nullptr;
+    c->side[0] = c->side[1] = nullptr;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int i = 0; i < 2; ++i) FOCK_CUDA(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi));
+    }
     slos_mu_init(c);
     {   // keep stream-ordered scratch (StreamScratch) in the pool between calls
         cudaMemPool_t pool;
@@ -125,6 +131,8 @@ extern "C" int fock_destroy(fock_ctx *c) {
     ScopedDevice sd(c->device);
     slos_mu_destroy(c);
     slos_thin_destroy(c);
+    for (int i = 0; i < 2; ++i)
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
     cudaFree(c->d_bt);
     cudaFree(c->d_dt);
     cudaFree(c->d_status);

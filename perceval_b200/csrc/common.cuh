@@ -23,6 +23,7 @@ struct fock_ctx {
     double *d_vacuum;  // constant complex 1 + 0i: SLOS layer 0 (the vacuum coefficient), written once at creation
     uint64_t launches;
     void *mu_state;    // owned by slos_mu.cu (cached tail occupation tables)
+    cudaStream_t side[2];           // high-priority side streams for the small launches of a layer (slos.cu: SideLaunch)
     cudaEvent_t ev_begin, ev_end;   // optional: recorded around every probability-layer launch (fock_profile_events)
 };
 

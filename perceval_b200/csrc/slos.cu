@@ -456,6 +456,45 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MINB) slos_tile_kernel(const 
 }
 
 // ---------------------------------------------------------------- host side
+// The small launches of a layer (the weight-0 sub-layer, the classes with tiles < 256 states: 222 CTAs that run 0.3 ms) go to
+// high-priority side streams of the context, forked from and joined to the caller's stream with per-call events, so that they
+// run under the main launch instead of before / after it with most SMs idle.
+struct SideLaunch {
+    fock_ctx *c;
+    cudaStream_t st;
+    cudaEvent_t fork = nullptr;
+    bool used[2] = {false, false};
+    SideLaunch(fock_ctx *c_, cudaStream_t st_) : c(c_), st(st_) {}
+    cudaStream_t stream(int i) {   // side stream i, ordered after everything enqueued on the caller's stream so far
+        if (!c->side[i]) return st;   // created with the context (fock_create)
+        if (!fork) {
+            if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return st;
+            cudaEventRecord(fork, st);
+        }
+        if (!used[i]) {
+            cudaStreamWaitEvent(c->side[i], fork, 0);
+            used[i] = true;
+        }
+        return c->side[i];
+    }
+    void join() {                  // the caller's stream continues after the side launches
+        for (int i = 0; i < 2; ++i)
+            if (used[i]) {
+                cudaEvent_t done;
+                if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess) {
+                    cudaEventRecord(done, c->side[i]);
+                    cudaStreamWaitEvent(st, done, 0);
+                    cudaEventDestroy(done);   // released when it has completed
+                } else {
+                    cudaStreamSynchronize(c->side[i]);
+                }
+                used[i] = false;
+            }
+        if (fork) { cudaEventDestroy(fork); fork = nullptr; }
+    }
+    ~SideLaunch() { join(); }
+};
+
 bool slos_thin_supports(int D, int k);           // slos_thin.cu
 int slos_thin_launch(fock_ctx *c, int D, TileArgs &a, bool want_child, bool want_probs, bool rangechk, unsigned grid, cudaStream_t st);
 int slos_mu_tuples(fock_ctx *c, int D, int u, uint32_t S, cudaStream_t st, const uint64_t **out);                   // slos_mu.cu
@@ -675,17 +714,18 @@ static int slos_layer_impl(fock_ctx *c, int m, int k, const double *d_U, int mk,
         const bool full = cb == 0 && ce == fock_count(m, k);
         const int Dsub = D > 0 ? slos_tail_modes(D) : 0;
         const bool sub0 = force == 0 && full && parent_full && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN && ((uintptr_t)d_parent & 15) == 0;
+        SideLaunch side(c, st);
         if (sub0) {
             const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1), cbase = fock_count(m, k) - S, pbase = fock_count(m, k - 1) - Sp;
             if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * pbase, 0, Sp, d_child ? d_child + 2 * cbase : nullptr,
-                                          d_probs ? d_probs + cbase : nullptr, d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX,
-                                          nullptr, false, m, m - D)) return rc;
+                                          d_probs ? d_probs + cbase : nullptr, d_sum, in_prodnfact, 0, S, side.stream(0), 0, UINT64_MAX,
+                                          UINT64_MAX, nullptr, false, m, m - D)) return rc;
         }
         const bool thin = force == 0 && d_probs != nullptr && D == 16 && m - D <= 8 && (ce - cb) >= (1ull << 25);
         if (D > 0 && thin && parent_full && slos_thin_supports(D, k) && ((uintptr_t)d_parent & 15) == 0) {
-            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1,
+            if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, side.stream(1), 2,
                                           UINT64_MAX, UINT64_MAX, nullptr, sub0)) return rc;
-            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 2,
+            return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 1,
                                     UINT64_MAX, UINT64_MAX, nullptr, sub0);
         }
         if (D > 0) return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, pb, pe, d_child, d_probs, d_sum, in_prodnfact, cb, ce, st, 0, gap_b, gap_e,
@@ -794,18 +834,21 @@ extern "C" int slos_layer_slab(fock_ctx *c, int m, int k, int p, const double *d
     // the weight-0 slab as a sub-layer on the tail modes (see slos_layer_impl)
     const int Dsub = slos_tail_modes(D);
     const bool sub0 = h_rho_ranges[1] > h_rho_ranges[0] && Dsub > 0 && fock_count(D, k) >= SLOS_SUB0_MIN;
+    SideLaunch side(c, st);
     if (sub0) {
         const uint64_t S = fock_count(D, k), Sp = fock_count(D, k - 1);
+        const bool only = children == S;
         if (int rc = slos_layer_tiles(c, Dsub, D, k, d_U, mk, d_parent + 2 * h_parent_slab_off[0], 0, Sp,
                                       d_child ? d_child + 2 * h_child_slab_off[0] : nullptr, d_probs ? d_probs + h_child_slab_off[0] : nullptr,
-                                      d_sum, in_prodnfact, 0, S, st, 0, UINT64_MAX, UINT64_MAX, nullptr, false, m, m - D)) return rc;
-        if (children == fock_count(D, k)) return FOCK_OK;
+                                      d_sum, in_prodnfact, 0, S, only ? st : side.stream(0), 0, UINT64_MAX, UINT64_MAX, nullptr, false, m,
+                                      m - D)) return rc;
+        if (only) return FOCK_OK;
     }
     const bool thin = d_probs != nullptr && D == 16 && m - D <= 8 && children >= (1ull << 24) && slos_thin_supports(D, k);
     if (thin) {
-        if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 1,
+        if (int rc = slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, side.stream(1), 2,
                                       UINT64_MAX, UINT64_MAX, &spec, sub0)) return rc;
-        return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 2, UINT64_MAX,
+        return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 1, UINT64_MAX,
                                 UINT64_MAX, &spec, sub0);
     }
     return slos_layer_tiles(c, D, m, k, d_U, mk, d_parent, 0, np, d_child, d_probs, d_sum, in_prodnfact, 0, nc, st, 0, UINT64_MAX,
