@@ -110,3 +110,33 @@ def test_balanced_boundaries(m, n, pieces):
     cost_eq = [P.chain_cost(P.plan_chain(m, n, equal[i], equal[i + 1])) for i in range(pieces)]
     assert max(cost) / (sum(cost) / pieces) <= max(cost_eq) / (sum(cost_eq) / pieces) + 1e-9
     assert bounds == P.balanced_boundaries(m, n, pieces)   # deterministic: every rank derives the same list
+
+
+def test_slab_plan_at_the_headline_sizes():
+    """SlabPlan at BASELINE's multi-GPU configs (host arithmetic only): ownership tiles the prefix space of every slab once,
+    what one rank receives is what the others send, the exchange groups of a rank carry its whole halo exactly once, the halo
+    of 12 photons / 24 modes stays below 1.6 GB per rank and step, and 14 photons / 28 modes fits 8 x 180 GB."""
+    from perceval_b200 import slab
+    for m, n, world, pieces in [(24, 12, 2, 1), (24, 12, 4, 1), (24, 12, 8, 1), (28, 14, 8, 4)]:
+        pl = slab.SlabPlan(m, n, world, pieces=pieces)
+        L = pl.layout
+        assert L.p == m - 16 and L.D == 16
+        for w in range(n + 1):
+            spans = sorted((a, b) for q in range(world) for ww, a, b in pl.own[q] if ww == w)
+            assert spans[0][0] == 0 and spans[-1][1] == L.nprefix[w] and all(x[1] == y[0] for x, y in zip(spans, spans[1:]))
+        recv = [pl.recv_elems(q) for q in range(world)]
+        send = [pl.send_elems(q) for q in range(world)]
+        assert sum(recv) == sum(send) and recv[0] == 0          # rank 0 holds the lowest prefix weights: every row it reads is its own
+        for q in range(world):
+            grouped = sum(ln for k in range(pl.k0, n) for g in range(pl.groups()) for s_ in range(world)
+                          for _, _, ln in pl.transfers(k, s_, q, g))
+            assert grouped == recv[q]
+        # every rank's share of the output layer within a factor 2 of the mean (the cost model trades states for transfer time)
+        shares = [pl.own_elems(n, q) / P.count(m, n) for q in range(world)]
+        assert abs(sum(shares) - 1.0) < 1e-12 and max(shares) < 2.0 / world
+        if (m, n) == (24, 12):
+            assert max(recv) * 16 < 1.6e9
+        else:
+            per_rank = [16 * sum(pl.buffer_elems(q)) + 8 * pl.own_elems(n, q) for q in range(world)]
+            assert max(per_rank) < 0.7 * 180e9, max(per_rank)
+            assert max(recv) * 16 < 60e9
