@@ -10,7 +10,10 @@
  * for this path (tests/test_oracle_golden.py replays reference tests/backends/test_backends.py:39-289,
  * docs naive.rst / slos.rst, the Boson_Bunching notebook known answers).  Clifford&Clifford sample
  * *sequences* are "parity unpinned" (exqalibur's RNG stream is unknowable); only the sampled distribution
- * is pinned (exact pmf by enumeration vs SLOS, see tests/test_cc2017_oracle.py).
+ * is pinned (exact pmf by enumeration vs SLOS, see tests/test_cc2017_oracle.py).  No reference test stores an
+ * amplitude beyond n = 8 or a permanent of a Haar sub-matrix: at the BASELINE sizes (n = 24 .. 32) the Glynn walk is
+ * "parity unpinned" by the reference and is instead arbitrated by the same walk in x87 extended precision
+ * (orc_glynn_range_ld; tests/test_oracle_golden.py, tests/test_gpu_parity.py).
  *
  * Every function cites the reference lines it restates (paths relative to /root/reference).
  *
